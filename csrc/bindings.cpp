@@ -1,0 +1,139 @@
+// Python bindings (torch extension) for the sm_100a kernels and the native runtime.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "kernels/kernels.h"
+
+namespace py = pybind11;
+using torch::Tensor;
+
+namespace ssb {
+void bind_runtime(py::module_& m);   // csrc/runtime/bindings_runtime.cpp
+}
+
+static void check_mat(const Tensor& t, const char* name) {
+    TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+    TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be fp32");
+    TORCH_CHECK(t.dim() == 2, name, " must be 2-D");
+    TORCH_CHECK(t.size(0) > 0 && t.size(1) > 0, name, " is empty");
+    TORCH_CHECK(t.stride(1) == 1 || t.size(1) == 1, name, " must have unit inner stride");
+}
+static int ld_of(const Tensor& t) { return (int)t.stride(0); }
+static void cuda_ok(cudaError_t e, const char* what) {
+    TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e));
+}
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+// y[rows, out] = relu?(x @ W^T + b)
+static void linear_fwd(const Tensor& x, const Tensor& W, const c10::optional<Tensor>& bias, int64_t bias_stride,
+                       bool relu, Tensor& y) {
+    check_mat(x, "x"); check_mat(W, "W"); check_mat(y, "y");
+    const int rows = x.size(0), in = x.size(1), out = W.size(0);
+    TORCH_CHECK(W.size(1) == in && y.size(0) == rows && y.size(1) == out, "linear_fwd: shape mismatch");
+    c10::cuda::CUDAGuard guard(x.device());
+    ssb::GemmPlan plan;
+    const char* err = ssb::gemm_plan_fwd(&plan, W.data_ptr<float>(), ld_of(W), x.data_ptr<float>(), ld_of(x),
+                                         y.data_ptr<float>(), ld_of(y), rows, in, out,
+                                         bias.has_value() ? bias->data_ptr<float>() : nullptr, (int)bias_stride, relu);
+    TORCH_CHECK(err == nullptr, "linear_fwd: ", err ? err : "");
+    cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_fwd launch");
+}
+
+// dx[rows, in] = (dz @ W) * (mask > 0)
+static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<Tensor>& mask, Tensor& dx) {
+    check_mat(dz, "dz"); check_mat(W, "W"); check_mat(dx, "dx");
+    const int rows = dz.size(0), out = dz.size(1), in = W.size(1);
+    TORCH_CHECK(W.size(0) == out && dx.size(0) == rows && dx.size(1) == in, "linear_dgrad: shape mismatch");
+    if (mask.has_value()) { check_mat(*mask, "mask"); TORCH_CHECK(mask->size(0) == rows && mask->size(1) == in, "mask shape"); }
+    c10::cuda::CUDAGuard guard(dz.device());
+    ssb::GemmPlan plan;
+    const char* err = ssb::gemm_plan_dgrad(&plan, W.data_ptr<float>(), ld_of(W), dz.data_ptr<float>(), ld_of(dz),
+                                           dx.data_ptr<float>(), ld_of(dx), rows, in, out,
+                                           mask.has_value() ? mask->data_ptr<float>() : nullptr,
+                                           mask.has_value() ? ld_of(*mask) : 0);
+    TORCH_CHECK(err == nullptr, "linear_dgrad: ", err ? err : "");
+    cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_dgrad launch");
+}
+
+// G[out, in] (+)= dz^T @ x ; db[out] (+)= colsum(dz) ; optionally W -= lr * (G + ...)
+static void linear_wgrad(const Tensor& dz, const Tensor& x, Tensor& G, bool accumulate, const c10::optional<Tensor>& db,
+                         int64_t db_stride, const c10::optional<Tensor>& W, double lr, bool fuse_sgd) {
+    check_mat(dz, "dz"); check_mat(x, "x"); check_mat(G, "G");
+    const int rows = dz.size(0), out = dz.size(1), in = x.size(1);
+    TORCH_CHECK(x.size(0) == rows && G.size(0) == out && G.size(1) == in, "linear_wgrad: shape mismatch");
+    c10::cuda::CUDAGuard guard(dz.device());
+    ssb::GemmPlan plan;
+    const char* err = ssb::gemm_plan_wgrad(&plan, dz.data_ptr<float>(), ld_of(dz), x.data_ptr<float>(), ld_of(x),
+                                           G.data_ptr<float>(), ld_of(G), rows, in, out, accumulate,
+                                           db.has_value() ? db->data_ptr<float>() : nullptr, (int)db_stride,
+                                           W.has_value() ? W->data_ptr<float>() : nullptr,
+                                           W.has_value() ? ld_of(*W) : 0, (float)lr, fuse_sgd);
+    TORCH_CHECK(err == nullptr, "linear_wgrad: ", err ? err : "");
+    cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_wgrad launch");
+}
+
+static void loss_head(const Tensor& logits, const c10::optional<Tensor>& target, const c10::optional<Tensor>& probs,
+                      const c10::optional<Tensor>& dlogits, const c10::optional<Tensor>& loss_out, double inv_batch) {
+    check_mat(logits, "logits");
+    c10::cuda::CUDAGuard guard(logits.device());
+    const int rows = logits.size(0), cols = logits.size(1);
+    cuda_ok(ssb::launch_loss_head(logits.data_ptr<float>(), ld_of(logits),
+                                  target.has_value() ? target->data_ptr<float>() : nullptr, target.has_value() ? ld_of(*target) : 0,
+                                  probs.has_value() ? probs->data_ptr<float>() : nullptr, probs.has_value() ? ld_of(*probs) : 0,
+                                  dlogits.has_value() ? dlogits->data_ptr<float>() : nullptr, dlogits.has_value() ? ld_of(*dlogits) : 0,
+                                  loss_out.has_value() ? loss_out->data_ptr<float>() : nullptr, rows, cols, (float)inv_batch,
+                                  cur_stream()), "loss_head");
+}
+
+static void softmax_grad(const Tensor& logits, const Tensor& upstream, Tensor& dlogits) {
+    check_mat(logits, "logits"); check_mat(upstream, "upstream"); check_mat(dlogits, "dlogits");
+    c10::cuda::CUDAGuard guard(logits.device());
+    cuda_ok(ssb::launch_softmax_grad(logits.data_ptr<float>(), ld_of(logits), upstream.data_ptr<float>(), ld_of(upstream),
+                                     dlogits.data_ptr<float>(), ld_of(dlogits), logits.size(0), logits.size(1), cur_stream()),
+            "softmax_grad");
+}
+
+static void relu_mask_(Tensor& g, const Tensor& y) {
+    check_mat(g, "g"); check_mat(y, "y");
+    c10::cuda::CUDAGuard guard(g.device());
+    cuda_ok(ssb::launch_relu_mask(g.data_ptr<float>(), ld_of(g), y.data_ptr<float>(), ld_of(y), g.size(0), g.size(1), cur_stream()), "relu_mask");
+}
+static void relu_fwd(const Tensor& x, Tensor& y) {
+    TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && x.numel() == y.numel());
+    c10::cuda::CUDAGuard guard(x.device());
+    cuda_ok(ssb::launch_relu_fwd(x.data_ptr<float>(), y.data_ptr<float>(), x.numel(), cur_stream()), "relu_fwd");
+}
+static void axpby(const Tensor& x, const Tensor& t, Tensor& y, double a, double b) {
+    TORCH_CHECK(x.is_contiguous() && t.is_contiguous() && y.is_contiguous() && x.numel() == y.numel() && t.numel() == y.numel());
+    c10::cuda::CUDAGuard guard(x.device());
+    cuda_ok(ssb::launch_axpby(x.data_ptr<float>(), t.data_ptr<float>(), y.data_ptr<float>(), (float)a, (float)b, x.numel(), cur_stream()), "axpby");
+}
+static void sgd_(Tensor& w, const Tensor& g, double lr) {
+    TORCH_CHECK(w.is_contiguous() && g.is_contiguous() && w.numel() == g.numel());
+    c10::cuda::CUDAGuard guard(w.device());
+    cuda_ok(ssb::launch_sgd(w.data_ptr<float>(), g.data_ptr<float>(), (float)lr, w.numel(), cur_stream()), "sgd");
+}
+static void argmax_correct(const Tensor& pred, const Tensor& target, Tensor& correct) {
+    check_mat(pred, "pred"); check_mat(target, "target");
+    TORCH_CHECK(correct.scalar_type() == torch::kInt32 && correct.is_cuda());
+    c10::cuda::CUDAGuard guard(pred.device());
+    cuda_ok(ssb::launch_argmax_correct(pred.data_ptr<float>(), ld_of(pred), target.data_ptr<float>(), ld_of(target),
+                                       pred.size(0), pred.size(1), correct.data_ptr<int>(), cur_stream()), "argmax_correct");
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "shallowspeed_b200 native module: sm_100a kernels + C++ pipeline runtime";
+    m.def("linear_fwd", &linear_fwd);
+    m.def("linear_dgrad", &linear_dgrad);
+    m.def("linear_wgrad", &linear_wgrad);
+    m.def("loss_head", &loss_head);
+    m.def("softmax_grad", &softmax_grad);
+    m.def("relu_mask_", &relu_mask_);
+    m.def("relu_fwd", &relu_fwd);
+    m.def("axpby", &axpby);
+    m.def("sgd_", &sgd_);
+    m.def("argmax_correct", &argmax_correct);
+    m.def("gemm_kernel_count", &ssb::gemm_kernel_count);
+    ssb::bind_runtime(m);
+}

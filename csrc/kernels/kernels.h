@@ -1,0 +1,88 @@
+// Host-side launch API of the hand-written sm_100a kernels (no torch dependency, so the
+// .cu files compile stand-alone with nvcc and the C++ runtime can call them directly).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace ssb {
+
+enum GemmMode : int { GEMM_FWD = 0, GEMM_DGRAD = 1, GEMM_WGRAD = 2 };
+
+// One description for the three Linear GEMMs.  Every GEMM is issued "swapped": the
+// FEATURE dimension sits on the tcgen05 M axis (128 TMEM lanes) and the skinny dimension
+// (micro-batch rows: 4..256) on the N axis, so a 4-row micro-batch costs an N=16 MMA
+// instead of a 128-row tile that is 97 % padding.
+//
+//   FWD   D[m=out, n=row] = sum_k W[m,k]  * X[n,k]      A=W   (K-major)  B=X  (K-major)
+//   DGRAD D[m=in,  n=row] = sum_k W[k,m]  * dZ[n,k]     A=W   (MN-major) B=dZ (K-major)
+//   WGRAD D[m=out, n=in ] = sum_k dZ[k,m] * X[k,n]      A=dZ  (MN-major) B=X  (MN-major)
+struct GemmParams {
+    int m_total, n_total, k_total;
+    int block_n;        // UMMA N: multiple of 16 (32 when B is MN-major), <= 256
+    int stages;         // smem pipeline depth
+    // FWD / DGRAD epilogue: out[n * ldo + m]
+    float* out;
+    int ldo;
+    const float* bias;  // FWD: + bias[m * bias_stride] (nullable)
+    int bias_stride;
+    int relu;           // FWD: max(.,0)
+    const float* mask;  // DGRAD: zero where mask[n * ldmask + m] <= 0 (nullable) - the ReLU
+    int ldmask;         //        backward of the PREVIOUS layer fused into this epilogue
+    // WGRAD epilogue: G[m * ldg + n] (+)= D ; db[m * db_stride] (+)= sum_k dZ[k, m]
+    float* G;
+    int ldg;
+    int accumulate;
+    float* db;          // nullable
+    int db_stride;
+    // WGRAD with the SGD update fused (single replica): W -= lr * (G_prev + D); G untouched
+    float* W;
+    int ldw;
+    float lr;
+    int fuse_sgd;
+};
+
+struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
+    CUtensorMap tmA, tmB;
+    GemmParams p;
+    int mode;
+    dim3 grid;
+    int smem_bytes;
+};
+
+// Build tensor maps + launch geometry.  All matrices are fp32 row-major with a leading
+// dimension that is a multiple of 4 floats and a 16-byte aligned base.
+//   FWD:   W[out, in] (ldw), X[rows, in] (ldx)            -> Y[rows, out] (ldy)
+//   DGRAD: W[out, in] (ldw), dZ[rows, out] (lddz)         -> dX[rows, in] (lddx)
+//   WGRAD: dZ[rows, out] (lddz), X[rows, in] (ldx)        -> G[out, in] (ldg)
+const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* X, int ldx, float* Y, int ldy,
+                          int rows, int in, int out, const float* bias, int bias_stride, int relu);
+const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float* dZ, int lddz, float* dX, int lddx,
+                            int rows, int in, int out, const float* mask, int ldmask);
+const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const float* X, int ldx, float* G, int ldg,
+                            int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
+                            float lr, int fuse_sgd);
+cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)
+
+// ---- small fused kernels --------------------------------------------------------------
+// logits[rows, cols] (ld) -> probs (nullable) ; training: dlogits (softmax-Jacobian x MSE
+// grad, 1/batch_size inside) and loss_out[0] = sum((t-p)^2)/batch_size.
+cudaError_t launch_loss_head(const float* logits, int ldl, const float* target, int ldt, float* probs, int ldp,
+                             float* dlogits, int ldd, float* loss_out, int rows, int cols, float inv_batch,
+                             cudaStream_t stream);
+// generic softmax backward for the functional API: dz = p*up - p*sum(p*up)
+cudaError_t launch_softmax_grad(const float* logits, int ldl, const float* upstream, int ldu, float* dlogits, int ldd,
+                                int rows, int cols, cudaStream_t stream);
+// g[r, c] = y[r, c] > 0 ? g[r, c] : 0   (stage-boundary ReLU backward)
+cudaError_t launch_relu_mask(float* g, int ldg, const float* y, int ldy, int rows, int cols, cudaStream_t stream);
+cudaError_t launch_relu_fwd(const float* x, float* y, long n, cudaStream_t stream);
+// y = a * x + b * t  (mse grad: a=2/B, b=-2/B)
+cudaError_t launch_axpby(const float* x, const float* t, float* y, float a, float b, long n, cudaStream_t stream);
+// w -= lr * g over a flat arena
+cudaError_t launch_sgd(float* w, const float* g, float lr, long n, cudaStream_t stream);
+// correct[0] += #rows with argmax(pred) == argmax(target)
+cudaError_t launch_argmax_correct(const float* pred, int ldp, const float* target, int ldt, int rows, int cols,
+                                  int* correct, cudaStream_t stream);
+
+}  // namespace ssb

@@ -1,0 +1,367 @@
+// tcgen05 / TMEM / TMA GEMM family for the Linear layer.
+//
+// One warp-specialised kernel, three instantiations (see GemmMode in kernels.h):
+//   warp 0    : TMA producer  - cp.async.bulk.tensor tiles (SWIZZLE_128B) into a ring of smem stages
+//   warp 1    : MMA issuer    - one thread issues tcgen05.mma.kind::tf32 (fp32 data, fp32 accumulate
+//                               in TMEM); tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2-5 : epilogue      - tcgen05.ld TMEM -> registers, fused bias / ReLU / ReLU-mask /
+//                               grad-accumulate / SGD, coalesced global stores.  During the WGRAD
+//                               main loop these warps also reduce db = colsum(dZ) straight from the
+//                               staged A tiles in shared memory (exact fp32, no extra pass over dZ).
+//
+// Operand staging (all tiles are 32 fp32 = 128 B wide, the SWIZZLE_128B span):
+//   K-major  tile: one TMA box [rows x 32 k]           -> 8-row groups 1024 B apart (SBO)
+//   MN-major tile: panels of  [32 k-rows x 32 mn]      -> 4096 B per panel (LBO), 4-k-row atoms 512 B (SBO);
+//                  32-bit MN-major operands require the SWIZZLE_128B_BASE32B flavour (TMA: 128B_ATOM_32B)
+// Ragged edges are handled by TMA out-of-bounds zero fill, so no dimension needs padding
+// beyond the 16-byte row pitch rule (the reference model's 127/126/125/123-wide layers).
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+
+namespace ssb {
+
+static constexpr int kThreads = 192;
+static constexpr uint32_t kBlockM = 128;
+static constexpr uint32_t kBlockK = 32;                 // fp32 elements = 128 B
+static constexpr uint32_t kABytes = kBlockM * 128;      // 16 KB per stage
+static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-rows x 128 B
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr bool A_MN = (MODE != GEMM_FWD);
+    constexpr bool B_MN = (MODE == GEMM_WGRAD);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
+    uint8_t* smem_gen = smem_raw + (smem_base - raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM;
+    const int n0 = blockIdx.y * p.block_n;
+    const int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
+    const uint32_t b_bytes = p.block_n * 128u;
+    const uint32_t stage_bytes = kABytes + b_bytes;
+    const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + 8u * (2 * p.stages) + 8u);
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+
+    const bool db_active = (MODE == GEMM_WGRAD) && (p.db != nullptr) && (blockIdx.y == 0);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), db_active ? 5 : 1);   // MMA commit (+ 4 db-reducing warps)
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                const uint32_t a_dst = smem_base + s * stage_bytes;
+                const uint32_t b_dst = a_dst + kABytes;
+                const int k0 = kb * kBlockK;
+                if (!A_MN) {
+                    tma_load_2d(a_dst, &tmA, full_bar(s), k0, m0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tma_load_2d(a_dst + i * kPanelBytes, &tmA, full_bar(s), m0 + 32 * i, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(b_dst, &tmB, full_bar(s), k0, n0);
+                } else {
+                    for (int j = 0; j < p.block_n / 32; ++j)
+                        tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(kBlockM, p.block_n, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + s * stage_bytes;
+                const uint32_t b_src = a_src + kABytes;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {         // UMMA_K = 8 for tf32
+                    const uint64_t adesc = A_MN ? umma_desc_mn_sw128_32b(a_src + k4 * 1024u, kPanelBytes, 512u)
+                                                : umma_desc_sw128(a_src + k4 * 32u, 16u, 1024u);
+                    const uint64_t bdesc = B_MN ? umma_desc_mn_sw128_32b(b_src + k4 * 1024u, kPanelBytes, 512u)
+                                                : umma_desc_sw128(b_src + k4 * 32u, 16u, 1024u);
+                    umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));                // smem stage free once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);                   // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                           // TMEM lane quarter this warp may read
+        const int m_local = q * 32 + lane;
+        const int m = m0 + m_local;
+        const bool m_ok = m < p.m_total;
+
+        float dbsum = 0.f;
+        if (MODE == GEMM_WGRAD && db_active) {
+            // db[m] = sum over micro-batch rows of dZ[row, m], read from the staged A panels.
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                mbar_wait(full_bar(s), ph);
+                const uint32_t panel = smem_base + s * stage_bytes + q * kPanelBytes;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    // SWIZZLE_128B_ATOM_32B: 32-byte chunk index ^= (row & 3)
+                    const uint32_t addr = panel + r * 128u + ((((uint32_t)lane >> 3) ^ (r & 3u)) << 5) + ((lane & 7u) << 2);
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+                    dbsum += v;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(s));
+            }
+        }
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        if (MODE == GEMM_FWD || MODE == GEMM_DGRAD) {
+            float bias = 0.f;
+            if (MODE == GEMM_FWD && p.bias != nullptr && m_ok) bias = p.bias[(size_t)m * p.bias_stride];
+            for (int c = 0; c < p.block_n; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!m_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < p.n_total) {
+                        float x = v[j] + bias;
+                        if (MODE == GEMM_FWD) {
+                            if (p.relu) x = fmaxf(x, 0.f);
+                        } else if (p.mask != nullptr) {
+                            x = (p.mask[(size_t)n * p.ldmask + m] > 0.f) ? x : 0.f;
+                        }
+                        p.out[(size_t)n * p.ldo + m] = x;     // lanes -> consecutive m: coalesced
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < p.block_n; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                if (!m_ok) continue;
+                const int nb = n0 + c;
+                float* grow = p.G + (size_t)m * p.ldg + nb;
+                float* wrow = p.fuse_sgd ? p.W + (size_t)m * p.ldw + nb : nullptr;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const int n = nb + 4 * g4;
+                    if (n + 3 < p.n_total) {
+                        float4 acc = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                        if (p.accumulate) {
+                            const float4 o = *reinterpret_cast<const float4*>(grow + 4 * g4);
+                            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                        }
+                        if (p.fuse_sgd) {
+                            float4 w = *reinterpret_cast<const float4*>(wrow + 4 * g4);
+                            w.x -= p.lr * acc.x; w.y -= p.lr * acc.y; w.z -= p.lr * acc.z; w.w -= p.lr * acc.w;
+                            *reinterpret_cast<float4*>(wrow + 4 * g4) = w;
+                        } else {
+                            *reinterpret_cast<float4*>(grow + 4 * g4) = acc;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (n + e < p.n_total) {
+                                float acc = v[4 * g4 + e];
+                                if (p.accumulate) acc += grow[4 * g4 + e];
+                                if (p.fuse_sgd) wrow[4 * g4 + e] -= p.lr * acc;
+                                else grow[4 * g4 + e] = acc;
+                            }
+                        }
+                    }
+                }
+            }
+            if (db_active && m_ok) {
+                float* dbp = p.db + (size_t)m * p.db_stride;
+                float acc = dbsum;
+                if (p.accumulate) acc += *dbp;
+                if (p.fuse_sgd) {
+                    float* bp = p.W + (size_t)m * p.ldw + (p.db - p.G);   // bias lives at the same offset in W
+                    *bp -= p.lr * acc;
+                } else {
+                    *dbp = acc;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// =========================================================================== host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [outer, inner] with pitch ld (floats); box = [box_outer, box_inner=32], SWIZZLE_128B.
+static const char* make_tmap(CUtensorMap* map, const float* base, int inner, int outer, int ld, int box_outer,
+                             bool mn_major = false) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return "cuTensorMapEncodeTiled entry point not available";
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return "TMA: base address must be 16-byte aligned";
+    if (ld % 4 != 0) return "TMA: leading dimension must be a multiple of 4 floats";
+    if (inner <= 0 || outer <= 0) return "TMA: empty tensor";
+    if (box_outer < 1 || box_outer > 256) return "TMA: box rows must be in [1, 256]";
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     // 32-bit MN-major UMMA operands only exist in the "128B swizzle, 32B atom" flavour
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
+}
+
+static int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+static void finish_plan(GemmPlan* plan) {
+    GemmParams& p = plan->p;
+    const int num_kb = (p.k_total + (int)kBlockK - 1) / (int)kBlockK;
+    const int stage_bytes = (int)kABytes + p.block_n * 128;
+    int stages = 200 * 1024 / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages > num_kb) stages = num_kb;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    plan->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2) + 16;
+    plan->grid = dim3((p.m_total + kBlockM - 1) / kBlockM, (p.n_total + p.block_n - 1) / p.block_n, 1);
+}
+
+const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* X, int ldx, float* Y, int ldy, int rows,
+                          int in, int out, const float* bias, int bias_stride, int relu) {
+    *plan = GemmPlan{};
+    plan->mode = GEMM_FWD;
+    GemmParams& p = plan->p;
+    p.m_total = out; p.n_total = rows; p.k_total = in;
+    p.block_n = rows >= 256 ? 256 : round_up_i(rows, 16);
+    p.out = Y; p.ldo = ldy; p.bias = bias; p.bias_stride = bias_stride; p.relu = relu;
+    if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, kBlockM)) return e;
+    if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, p.block_n)) return e;
+    finish_plan(plan);
+    return nullptr;
+}
+
+const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float* dZ, int lddz, float* dX, int lddx,
+                            int rows, int in, int out, const float* mask, int ldmask) {
+    *plan = GemmPlan{};
+    plan->mode = GEMM_DGRAD;
+    GemmParams& p = plan->p;
+    p.m_total = in; p.n_total = rows; p.k_total = out;
+    p.block_n = rows >= 256 ? 256 : round_up_i(rows, 16);
+    p.out = dX; p.ldo = lddx; p.mask = mask; p.ldmask = ldmask;
+    if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, 32, true)) return e;          // MN-major panels [32 k x 32 m]
+    if (const char* e = make_tmap(&plan->tmB, dZ, out, rows, lddz, p.block_n)) return e;
+    finish_plan(plan);
+    return nullptr;
+}
+
+const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const float* X, int ldx, float* G, int ldg,
+                            int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
+                            float lr, int fuse_sgd) {
+    *plan = GemmPlan{};
+    plan->mode = GEMM_WGRAD;
+    GemmParams& p = plan->p;
+    p.m_total = out; p.n_total = in; p.k_total = rows;
+    p.block_n = in >= 128 ? 128 : round_up_i(in, 32);
+    p.G = G; p.ldg = ldg; p.accumulate = accumulate; p.db = db; p.db_stride = db_stride;
+    p.W = W; p.ldw = ldw; p.lr = lr; p.fuse_sgd = fuse_sgd;
+    if (fuse_sgd && W == nullptr) return "fuse_sgd needs W";
+    if (const char* e = make_tmap(&plan->tmA, dZ, out, rows, lddz, 32, true)) return e;
+    if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, 32, true)) return e;
+    finish_plan(plan);
+    return nullptr;
+}
+
+static std::atomic<int> g_launches{0};
+int gemm_kernel_count() { return g_launches.load(); }
+
+template <int MODE>
+static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
+    static int configured = 0;
+    if (configured < plan.smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = 220 * 1024;
+    }
+    tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+    switch (plan.mode) {
+        case GEMM_FWD: return launch_mode<GEMM_FWD>(plan, stream);
+        case GEMM_DGRAD: return launch_mode<GEMM_DGRAD>(plan, stream);
+        case GEMM_WGRAD: return launch_mode<GEMM_WGRAD>(plan, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ssb

@@ -1,0 +1,156 @@
+"""Schedule tests: instruction membership (the reference's tests/test_schedules.py
+strategy) PLUS what that file's header asks for and never got: happens-before predicates,
+deadlock freedom under rendezvous semantics, slot liveness, for every schedule."""
+import pytest
+
+from shallowspeed_b200 import pipe
+from shallowspeed_b200.parallel.instructions import flatten
+from shallowspeed_b200.parallel.validate import ScheduleError, max_in_flight, simulate, validate
+from shallowspeed_b200.pipe import (GPipeSchedule, InferenceSchedule, NaiveParallelSchedule,
+                                    PipeDreamSchedule)
+
+TRAIN_SCHEDULES = [NaiveParallelSchedule, GPipeSchedule, PipeDreamSchedule]
+
+
+def cmd_is_in(cmd_t, sched):
+    return any(isinstance(x, cmd_t) for x in flatten(sched) if True) if sched and isinstance(sched[0], list) else any(
+        isinstance(x, cmd_t) for x in sched)
+
+
+def render(sc):
+    ab = {"ZeroGrad": "Z", "OptimizerStep": "OPT", "LoadMuBatchInput": "LX", "LoadMuBatchTarget": "LY",
+          "Forward": "F", "BackwardGradAcc": "B", "BackwardGradAllReduce": "B+AR", "SendActivations": "SA",
+          "RecvActivations": "RA", "SendInputGrad": "SG", "RecvOutputGrad": "RG"}
+    return " | ".join(" ".join(ab[type(i).__name__] + (str(i.mubatch_id) if hasattr(i, "mubatch_id") else "")
+                               for i in t) for t in sc.steps())
+
+
+def test_naive_dp_only():
+    cmds = list(NaiveParallelSchedule(num_micro_batches=5, num_stages=1, stage_id=0).steps())
+    assert cmd_is_in(pipe.ZeroGrad, cmds[0]) and not cmd_is_in(pipe.ZeroGrad, cmds[1:])
+    assert cmd_is_in(pipe.BackwardGradAllReduce, cmds[-2]) and not cmd_is_in(pipe.BackwardGradAllReduce, cmds[:-2])
+    assert cmd_is_in(pipe.OptimizerStep, cmds[-1]) and not cmd_is_in(pipe.OptimizerStep, cmds[:-1])
+
+
+def test_reference_streams_are_reproduced():
+    # the verified streams of the reference, M=3, S=3
+    assert render(NaiveParallelSchedule(3, 3, 0)) == "Z | LX0 F0 SA RG B0 | LX1 F1 SA RG B1 | LX2 F2 SA RG B+AR2 | OPT"
+    assert render(NaiveParallelSchedule(3, 3, 1)) == "Z | RA F0 SA RG B0 SG | RA F1 SA RG B1 SG | RA F2 SA RG B+AR2 SG | OPT"
+    assert render(NaiveParallelSchedule(3, 3, 2)) == "Z | RA F0 LY0 B0 SG | RA F1 LY1 B1 SG | RA F2 LY2 B+AR2 SG | OPT"
+    assert render(GPipeSchedule(3, 3, 0)) == "Z | LX0 F0 SA | LX1 F1 SA | LX2 F2 SA | RG B2 | RG B1 | RG B+AR0 | OPT"
+    assert render(GPipeSchedule(3, 3, 1)) == "Z | RA F0 SA | RA F1 SA | RA F2 SA | RG B2 SG | RG B1 SG | RG B+AR0 SG | OPT"
+    assert render(GPipeSchedule(3, 3, 2)) == "Z | RA F0 | RA F1 | RA F2 | LY2 B2 SG | LY1 B1 SG | LY0 B+AR0 SG | OPT"
+    assert render(InferenceSchedule(2, 3, 0)) == "LX0 F0 SA | LX1 F1 SA"
+    assert render(InferenceSchedule(2, 3, 1)) == "RA F0 SA | RA F1 SA"
+    assert render(InferenceSchedule(2, 3, 2)) == "RA F0 | RA F1"
+    assert render(NaiveParallelSchedule(3, 1, 0)) == "Z | LX0 F0 LY0 B0 | LX1 F1 LY1 B1 | LX2 F2 LY2 B+AR2 | OPT"
+    assert render(GPipeSchedule(3, 1, 0)) == "Z | LX0 F0 | LX1 F1 | LX2 F2 | LY2 B2 | LY1 B1 | LY0 B+AR0 | OPT"
+
+
+def test_first_stage_loads_inputs_never_targets_middle_has_all_comm():
+    for cls in TRAIN_SCHEDULES:
+        first = flatten(list(cls(4, 3, 0).steps()))
+        assert cmd_is_in(pipe.LoadMuBatchInput, first) and not cmd_is_in(pipe.LoadMuBatchTarget, first)
+        assert not cmd_is_in(pipe.RecvActivations, first) and not cmd_is_in(pipe.SendInputGrad, first)
+        mid = flatten(list(cls(4, 3, 1).steps()))
+        for t in (pipe.RecvActivations, pipe.SendActivations, pipe.RecvOutputGrad, pipe.SendInputGrad):
+            assert cmd_is_in(t, mid)
+        assert not cmd_is_in(pipe.LoadInstruction, mid)
+        last = flatten(list(cls(4, 3, 2).steps()))
+        assert cmd_is_in(pipe.LoadMuBatchTarget, last) and not cmd_is_in(pipe.SendActivations, last)
+
+
+@pytest.mark.parametrize("cls", TRAIN_SCHEDULES + [InferenceSchedule])
+@pytest.mark.parametrize("S", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("M", [1, 2, 4, 7, 16])
+def test_schedule_is_valid_and_deadlock_free(cls, S, M):
+    validate(cls, M, S)
+
+
+def _F(mu):
+    return lambda i: isinstance(i, pipe.Forward) and i.mubatch_id == mu
+
+
+def _B(mu):
+    return lambda i: isinstance(i, (pipe.BackwardGradAcc, pipe.BackwardGradAllReduce)) and i.mubatch_id == mu
+
+
+def test_happens_before_naive():
+    # naive: BWD of mubatch 1 completes before FWD of mubatch 2, on every stage pair
+    tr = validate(NaiveParallelSchedule, 4, 3)
+    for s in range(3):
+        assert tr.happens_before((s, _B(1)), (s, _F(2)))
+    assert tr.happens_before((0, _B(1)), (2, _F(2)))       # even across stages
+    assert tr.happens_before((2, _B(0)), (0, _B(0)))       # gradients flow last -> first
+
+
+def test_happens_before_gpipe():
+    # gpipe: FWD of the LAST mubatch precedes BWD of any mubatch; backward order is reversed
+    tr = validate(GPipeSchedule, 4, 3)
+    for s in range(3):
+        for mu in range(4):
+            assert tr.happens_before((s, _F(3)), (s, _B(mu)))
+        assert tr.happens_before((s, _B(3)), (s, _B(0)))
+
+
+def test_happens_before_1f1b():
+    M, S = 8, 4
+    tr = validate(PipeDreamSchedule, M, S)
+    # last stage alternates F, B from the start; first stage runs S-1 warm-up forwards
+    assert tr.happens_before((S - 1, _B(0)), (S - 1, _F(1)))
+    assert tr.happens_before((0, _F(S - 1)), (0, _B(0)))
+    assert tr.happens_before((0, _B(0)), (0, _F(S)))          # steady state: 1F1B
+    for s in range(S):                                        # backward in order, AR on the last one
+        assert tr.happens_before((s, _B(M - 2)), (s, _B(M - 1)))
+        fl = flatten(list(PipeDreamSchedule(M, S, s).steps()))
+        ar = [i for i in fl if isinstance(i, pipe.BackwardGradAllReduce)]
+        assert len(ar) == 1 and ar[0].mubatch_id == M - 1
+
+
+def test_activation_stash_bounds():
+    M, S = 16, 4
+    for s in range(S):
+        assert max_in_flight(NaiveParallelSchedule(M, S, s)) == 1
+        assert max_in_flight(GPipeSchedule(M, S, s)) == M
+        pd = PipeDreamSchedule(M, S, s)
+        assert max_in_flight(pd) == S - s == pd.num_slots     # bounded by depth, not by M
+        assert pd.num_buffers == 2 * pd.num_slots and pd.num_buffers % 2 == 0
+    assert PipeDreamSchedule(2, 8, 0).num_slots == 2           # never more than M
+
+
+def test_validator_catches_broken_schedules():
+    class SendsFirst(GPipeSchedule):            # both neighbours send before anyone receives
+        def _lower_forward(self, mu):
+            cmds = super()._lower_forward(mu)
+            return cmds
+
+        def steps(self):
+            for tick in super().steps():
+                yield [c for c in tick if not isinstance(c, pipe.RecvActivations)]
+
+    with pytest.raises(ScheduleError):
+        simulate([SendsFirst(2, 2, s) for s in range(2)])
+
+    class ReusesSlot(GPipeSchedule):            # all mubatches in slot 0 although they are stashed
+        def slot(self, mu):
+            return 0
+
+    with pytest.raises(ScheduleError):
+        simulate([ReusesSlot(3, 2, s) for s in range(2)])
+
+    class BackwardFirst(NaiveParallelSchedule):
+        def compute_ticks(self):
+            return [[("B", 0), ("F", 0)]]
+
+    with pytest.raises(ScheduleError):
+        simulate([BackwardFirst(1, 1, 0)])
+
+
+def test_instruction_encoding_roundtrip():
+    from shallowspeed_b200.parallel.instructions import ALL_INSTRUCTIONS, OPCODE_TO_CLS, encode
+
+    assert len(ALL_INSTRUCTIONS) == 11 and len(OPCODE_TO_CLS) == 11
+    for ins in flatten(list(PipeDreamSchedule(4, 3, 1).steps())):
+        op, b, mu = encode(ins)
+        assert OPCODE_TO_CLS[op] is type(ins)
+        assert b == getattr(ins, "buffer_id", -1) and mu == getattr(ins, "mubatch_id", -1)
