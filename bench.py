@@ -1,0 +1,218 @@
+#!/usr/bin/env python
+"""Headline benchmark: MLP training throughput (samples/s, whole job) on the reference's
+default workload - MLP 784-128-127-126-125-124-123-10, 4 micro-batches, SGD lr 0.006
+ - data parallel over N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+* ``value``  : device-timed (CUDA events on the engine's stream, barrier + synchronize on
+               both sides, MAX over ranks) with every step's inputs copied from a
+               device-resident pool larger than L2.
+* ``e2e``    : the same K steps through the public ``Trainer.step`` API with each step's
+               inputs copied from PINNED HOST memory (H2D) and its loss read back (D2H).
+* scaling    : weak - the per-GPU batch stays at the reference's 128 samples (4 x 32 rows),
+               global batch = 128 x N.  ``--scaling strong`` keeps the global batch at 128.
+* ``--impl reference`` runs the unmodified reference (NumPy on the host CPUs, mpi4py shim)
+               on the same config; N ranks = N processes.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYER_SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
+PER_GPU_BATCH = 128
+N_MUBATCHES = 4
+LR = 0.006
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
+    ap.add_argument("--schedule", default="naive")
+    ap.add_argument("--comm", choices=["fused", "nccl"], default="fused")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pool-batches", type=int, default=352, help="distinct batches in the input pool (352 x 401 KB = 141 MB > L2)")
+    return ap.parse_args()
+
+
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` without torchrun: re-exec under torch.distributed.run."""
+    import subprocess
+
+    port = 29700 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    sys.exit(subprocess.call(cmd))
+
+
+def global_batch(args):
+    return PER_GPU_BATCH * args.gpus if args.scaling == "weak" else PER_GPU_BATCH
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args):
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_reference as rr
+
+    if not rr.reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed (pip --target baseline/_ref /root/reference)"}))
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    gbs = global_batch(args)
+    data_dir = os.path.join(ROOT, "baseline", "_ref", "data", "mnist_784")
+    if rank == 0:
+        from shallowspeed_b200.dataset import write_reference_files
+
+        write_reference_files(data_dir)
+    if args.gpus > 1:   # everyone waits for rank 0's files
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "mpi_shim"))
+        from mpi4py import MPI
+
+        MPI.COMM_WORLD.Barrier()
+    res = rr.main(["--dp", str(args.gpus), "--pp", "1", "--schedule", "naive", "--steps", str(args.steps),
+                   "--warmup", str(args.warmup), "--global-batch-size", str(gbs), "--n-mubatches", str(N_MUBATCHES),
+                   "--data-dir", data_dir])
+    if res is not None:
+        print(json.dumps({
+            "impl": "reference", "metric": "MLP training samples/sec (whole job)", "value": res["samples_per_s"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic MNIST-shaped (reference file format), random-init weights",
+            "e2e": {"value": res["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "config": {"model": "MLP 784-128-127-126-125-124-123-10", "global_batch": gbs, "n_mubatches": N_MUBATCHES,
+                       "parallelism": f"dp{args.gpus}", "device": "host CPUs (NumPy + mpi4py shim over gloo)",
+                       "threads_per_rank": res["threads_per_rank"], "weights_dtype": res["weights_dtype"],
+                       "timing": "wall clock between barriers, max over ranks (CPU code)"},
+        }))
+
+
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.comm import ProcessGrid, SelfComm, make_torch_comms
+    from shallowspeed_b200.parallel.engine import Trainer
+    from shallowspeed_b200.utils.timing import ClockSampler, max_over_ranks
+
+    world = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        grid = ProcessGrid(world, 1, rank)
+        dp_comm, pp_comm = make_torch_comms(grid)
+    else:
+        grid, dp_comm, pp_comm = ProcessGrid(1, 1, 0), None, None
+
+    gbs = global_batch(args)
+    local_bs = gbs // world
+    trainer = Trainer(LAYER_SIZES, global_batch_size=gbs, n_mubatches=N_MUBATCHES, lr=LR, schedule=args.schedule,
+                      dp_comm=dp_comm, pp_comm=pp_comm, grid=grid, comm_mode=args.comm, use_graph=not args.no_graph,
+                      device=dev)
+    eng = trainer.engine
+
+    # input pools: this rank's shard of `pool` distinct global batches
+    pool = args.pool_batches
+    x, y = synthetic_mnist(n=pool * gbs)
+    xs = torch.from_numpy(x[rank::world].copy()).reshape(pool, local_bs, 784)
+    ys = torch.from_numpy(y[rank::world].copy()).reshape(pool, local_bs, 10)
+    x_host, y_host = xs.pin_memory(), ys.pin_memory()
+    x_dev, y_dev = xs.to(dev), ys.to(dev)
+    h2d = x_host[0].numel() * 4 + y_host[0].numel() * 4
+    d2h = 4 * N_MUBATCHES
+
+    stream = torch.cuda.ExternalStream(eng.main_stream(), device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(n):
+            step_fn(i)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def dev_step(i):
+        j = i % pool
+        trainer.step_async(x_dev[j], y_dev[j])
+
+    losses = []
+
+    def e2e_step(i):
+        j = i % pool
+        losses.append(trainer.step(x_host[j], y_host[j]))      # H2D inputs + D2H loss every step
+
+    for i in range(args.warmup):
+        dev_step(i)
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(lambda i: dev_step(args.warmup + i), args.steps)
+        for i in range(max(3, args.warmup // 4)):
+            e2e_step(i)
+        ms_e2e = timed(lambda i: e2e_step(args.warmup + i), args.steps)
+    ms_dev, ms_e2e = max_over_ranks(ms_dev, dev), max_over_ranks(ms_e2e, dev)
+    clocks = clk.summary()
+
+    if world > 1:   # replicas must still be bit-identical after the run
+        from shallowspeed_b200.utils import assert_sync, get_model_hash
+
+        trainer.synchronize()
+        assert_sync(dp_comm, get_model_hash(trainer.model))
+    if rank == 0:
+        value = args.steps * gbs / (ms_dev * 1e-3)
+        e2e = args.steps * gbs / (ms_e2e * 1e-3)
+        kps = int(eng.kernels_per_step())
+        print(json.dumps({
+            "impl": "ours", "metric": "MLP training samples/sec (whole job)", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "tf32 tensor-core products, fp32 storage + fp32 accumulate (reference contract: fp32)",
+            "data": "synthetic MNIST-shaped, random-init weights",
+            "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": kps * args.steps,
+            "clocks": clocks,
+            "config": {"model": "MLP 784-128-127-126-125-124-123-10", "global_batch": gbs, "per_gpu_batch": local_bs,
+                       "n_mubatches": N_MUBATCHES, "seq_len": None, "parallelism": f"dp{world}", "schedule": args.schedule,
+                       "dp_comm": args.comm if world > 1 else "none", "cuda_graph": not args.no_graph,
+                       "kernels_per_step": kps, "graph_nodes": int(eng.graph_nodes()),
+                       "l2": f"inputs cycle through a pool of {pool} distinct batches ({pool * h2d / 1e6:.0f} MB > 126 MB L2); "
+                             "the 0.7 MB of weights are legitimately L2-resident across steps",
+                       "last_loss": losses[-1] if losses else None},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        relaunch_under_torchrun(args)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

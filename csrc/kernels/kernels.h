@@ -63,6 +63,7 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
                             int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
                             float lr, int fuse_sgd);
 cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+cudaError_t gemm_configure();   // opt every instantiation into > 48 KB dynamic smem (call outside graph capture)
 int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)
 
 // ---- small fused kernels --------------------------------------------------------------

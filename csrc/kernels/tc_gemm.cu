@@ -342,13 +342,24 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
 static std::atomic<int> g_launches{0};
 int gemm_kernel_count() { return g_launches.load(); }
 
+static constexpr int kMaxDynSmem = 220 * 1024;
+static bool g_configured = false;
+
+cudaError_t gemm_configure() {
+    if (g_configured) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    g_configured = true;
+    return cudaSuccess;
+}
+
 template <int MODE>
 static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
-    static int configured = 0;
-    if (configured < plan.smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (!g_configured) {
+        cudaError_t e = gemm_configure();
         if (e != cudaSuccess) return e;
-        configured = 220 * 1024;
     }
     tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.p);
     g_launches.fetch_add(1, std::memory_order_relaxed);

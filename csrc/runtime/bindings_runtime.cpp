@@ -1,5 +1,166 @@
-#include <pybind11/pybind11.h>
+// pybind11 face of the native runtime: NCCL communicators + PipeEngine.
+#include <torch/extension.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <nccl.h>
+
+#include "runtime/pipe_engine.h"
+
 namespace py = pybind11;
+
 namespace ssb {
-void bind_runtime(py::module_& m) { (void)m; }
+
+#define NCCL_OK(expr)                                                                              \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        TORCH_CHECK(_r == ncclSuccess, "NCCL error: ", ncclGetErrorString(_r), " at " #expr);      \
+    } while (0)
+
+// Own NCCL communicator (not torch's ProcessGroup): the C++ executor issues ncclSend/Recv/
+// AllReduce itself on its own streams, inside CUDA-graph capture.
+class NcclComm {
+public:
+    static py::bytes unique_id() {
+        ncclUniqueId id;
+        NCCL_OK(ncclGetUniqueId(&id));
+        return py::bytes(reinterpret_cast<const char*>(&id), sizeof(id));
+    }
+    NcclComm(const std::string& id_bytes, int nranks, int rank) : nranks_(nranks), rank_(rank) {
+        TORCH_CHECK(id_bytes.size() == sizeof(ncclUniqueId), "bad ncclUniqueId size");
+        ncclUniqueId id;
+        memcpy(&id, id_bytes.data(), sizeof(id));
+        NCCL_OK(ncclCommInitRank(&comm_, nranks, id, rank));
+    }
+    ~NcclComm() {
+        if (comm_) ncclCommDestroy(comm_);
+    }
+    // open the channels now so the first captured step does not pay for it
+    void warmup() {
+        float* buf = nullptr;
+        cudaMalloc(&buf, 1024);
+        cudaMemset(buf, 0, 1024);
+        NCCL_OK(ncclAllReduce(buf, buf, 256, ncclFloat, ncclSum, comm_, nullptr));
+        if (nranks_ > 1) {
+            NCCL_OK(ncclGroupStart());
+            const int next = (rank_ + 1) % nranks_, prev = (rank_ + nranks_ - 1) % nranks_;
+            NCCL_OK(ncclSend(buf, 64, ncclFloat, next, comm_, nullptr));
+            NCCL_OK(ncclRecv(buf + 128, 64, ncclFloat, prev, comm_, nullptr));
+            NCCL_OK(ncclGroupEnd());
+        }
+        cudaStreamSynchronize(nullptr);
+        cudaFree(buf);
+    }
+    ncclComm_t get() const { return comm_; }
+    int nranks() const { return nranks_; }
+    int rank() const { return rank_; }
+
+private:
+    ncclComm_t comm_ = nullptr;
+    int nranks_, rank_;
+};
+
+static torch::Tensor view_of(float* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA, dev);
+    return torch::from_blob(ptr, {rows, cols}, {ld, 1}, [](void*) {}, opts);
+}
+
+class PyEngine {
+public:
+    PyEngine(const std::vector<std::tuple<int, int, int, int64_t, int>>& layers, py::dict cfg, torch::Tensor weights,
+             torch::Tensor grads)
+        : weights_(weights), grads_(grads) {
+        TORCH_CHECK(weights.is_cuda() && grads.is_cuda() && weights.is_contiguous() && grads.is_contiguous());
+        TORCH_CHECK(weights.scalar_type() == torch::kFloat32 && grads.scalar_type() == torch::kFloat32);
+        EngineConfig c;
+        for (auto& t : layers) c.layers.push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t), std::get<3>(t), std::get<4>(t)});
+        auto geti = [&](const char* k, int dflt) { return cfg.contains(k) ? cfg[k].cast<int>() : dflt; };
+        c.is_first = geti("is_first", 1); c.is_last = geti("is_last", 1);
+        c.stage = geti("stage", 0); c.n_stages = geti("n_stages", 1);
+        c.mb_rows = geti("mb_rows", 32); c.n_mu = geti("n_mu", 4); c.global_batch = geti("global_batch", 128);
+        c.lr = cfg.contains("lr") ? cfg["lr"].cast<float>() : 0.006f;
+        c.training = geti("training", 1); c.use_graph = geti("use_graph", 1);
+        c.dp_size = geti("dp_size", 1); c.dp_rank = geti("dp_rank", 0); c.dp_mode = geti("dp_mode", 0);
+        c.in_dim = geti("in_dim", 784); c.out_dim = geti("out_dim", 10);
+        c10::cuda::CUDAGuard guard(weights.device());
+        engine_ = std::make_unique<PipeEngine>(c, weights.data_ptr<float>(), grads.data_ptr<float>(), weights.numel());
+    }
+    void set_pp_comm(std::shared_ptr<NcclComm> c) { pp_ = c; engine_->set_pp_comm(c->get()); }
+    void set_dp_comm(std::shared_ptr<NcclComm> c) { dp_ = c; engine_->set_dp_comm(c->get()); }
+    void build(const std::vector<std::tuple<int, int, int>>& instrs) {
+        c10::cuda::CUDAGuard guard(weights_.device());
+        engine_->build(instrs);
+    }
+    void stage_inputs(const c10::optional<torch::Tensor>& x, const c10::optional<torch::Tensor>& y) {
+        const auto& cfg = engine_->config();
+        const int64_t rows = (int64_t)cfg.n_mu * cfg.mb_rows;
+        bool from_host = false;
+        const float *xp = nullptr, *yp = nullptr;
+        if (x.has_value()) {
+            TORCH_CHECK(x->is_contiguous() && x->scalar_type() == torch::kFloat32 && x->numel() == rows * cfg.in_dim, "x shape");
+            xp = x->data_ptr<float>(); from_host = !x->is_cuda();
+        }
+        if (y.has_value()) {
+            TORCH_CHECK(y->is_contiguous() && y->scalar_type() == torch::kFloat32 && y->numel() == rows * cfg.out_dim, "y shape");
+            yp = y->data_ptr<float>(); from_host = !y->is_cuda();
+        }
+        engine_->stage_inputs(xp, yp, from_host);
+    }
+    void run() { engine_->run(); }
+    void synchronize() { engine_->synchronize(); }
+    float last_loss() { return engine_->last_loss(); }
+    int count_correct() { return engine_->count_correct(); }
+    void reset_correct() { engine_->reset_correct(); }
+    torch::Tensor act(int mu, int l) {
+        const auto& cfg = engine_->config();
+        const int cols = l == 0 ? cfg.layers[0].in : cfg.layers[l - 1].out;
+        return view_of(engine_->act_ptr(mu, l), cfg.mb_rows, cols, engine_->act_ld(l));
+    }
+    torch::Tensor dz(int mu, int l) {
+        const auto& cfg = engine_->config();
+        const int cols = l == 0 ? cfg.layers[0].in : cfg.layers[l - 1].out;
+        return view_of(engine_->dz_ptr(mu, l), cfg.mb_rows, cols, engine_->act_ld(l));
+    }
+    torch::Tensor probs(int mu) {
+        const auto& cfg = engine_->config();
+        return view_of(engine_->probs_ptr(mu), cfg.mb_rows, cfg.out_dim, engine_->act_ld((int)cfg.layers.size()));
+    }
+    int64_t kernels_per_step() { return engine_->kernels_per_step(); }
+    int64_t graph_nodes() { return engine_->graph_nodes(); }
+    int64_t main_stream() { return reinterpret_cast<int64_t>(engine_->main_stream()); }
+    std::string describe() { return engine_->describe(); }
+
+private:
+    torch::Tensor weights_, grads_;
+    std::shared_ptr<NcclComm> pp_, dp_;
+    std::unique_ptr<PipeEngine> engine_;
+};
+
+void bind_runtime(py::module_& m) {
+    py::class_<NcclComm, std::shared_ptr<NcclComm>>(m, "NcclComm")
+        .def_static("unique_id", &NcclComm::unique_id)
+        .def(py::init<const std::string&, int, int>())
+        .def("warmup", &NcclComm::warmup)
+        .def("nranks", &NcclComm::nranks)
+        .def("rank", &NcclComm::rank);
+    py::class_<PyEngine>(m, "PipeEngine")
+        .def(py::init<const std::vector<std::tuple<int, int, int, int64_t, int>>&, py::dict, torch::Tensor, torch::Tensor>())
+        .def("set_pp_comm", &PyEngine::set_pp_comm)
+        .def("set_dp_comm", &PyEngine::set_dp_comm)
+        .def("build", &PyEngine::build)
+        .def("stage_inputs", &PyEngine::stage_inputs)
+        .def("run", &PyEngine::run)
+        .def("synchronize", &PyEngine::synchronize)
+        .def("last_loss", &PyEngine::last_loss)
+        .def("count_correct", &PyEngine::count_correct)
+        .def("reset_correct", &PyEngine::reset_correct)
+        .def("act", &PyEngine::act)
+        .def("dz", &PyEngine::dz)
+        .def("probs", &PyEngine::probs)
+        .def("kernels_per_step", &PyEngine::kernels_per_step)
+        .def("graph_nodes", &PyEngine::graph_nodes)
+        .def("main_stream", &PyEngine::main_stream)
+        .def("describe", &PyEngine::describe);
+}
+
 }  // namespace ssb

@@ -1,0 +1,454 @@
+#include "runtime/pipe_engine.h"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <sstream>
+#include <stdexcept>
+
+namespace ssb {
+
+#define CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+    } while (0)
+#define NCCL_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        ncclResult_t _r = (expr);                                                                          \
+        if (_r != ncclSuccess)                                                                             \
+            throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(_r) + " at " #expr); \
+    } while (0)
+
+// opcodes of shallowspeed_b200/parallel/instructions.py
+enum : int {
+    I_ZERO_GRAD = 0, I_OPT_STEP = 1, I_RECV_ACT = 2, I_SEND_ACT = 3, I_RECV_GRAD = 4, I_SEND_GRAD = 5,
+    I_FORWARD = 6, I_BWD_ACC = 7, I_BWD_AR = 8, I_LOAD_X = 9, I_LOAD_Y = 10
+};
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, int64_t arena_numel)
+    : cfg_(cfg), W_(weights), G_(grads), arena_numel_(arena_numel), L_((int)cfg.layers.size()) {
+    n_mu_streams_ = std::max(1, std::min(cfg_.n_mu, 4));
+    n_w_streams_ = std::max(1, std::min(L_, 4));
+    const int n_streams = 1 + n_mu_streams_ + n_w_streams_ + 2;
+    s_comm_ = 1 + n_mu_streams_ + n_w_streams_;
+    s_dp_ = s_comm_ + 1;
+    streams_.resize(n_streams);
+    for (auto& s : streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    alloc_buffers();
+}
+
+PipeEngine::~PipeEngine() {
+    cudaDeviceSynchronize();
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    if (graph_) cudaGraphDestroy(graph_);
+    for (auto e : events_) cudaEventDestroy(e);
+    for (auto s : streams_) cudaStreamDestroy(s);
+    for (auto p : owned_) cudaFree(p);
+    if (loss_host_) cudaFreeHost(loss_host_);
+}
+
+void PipeEngine::alloc_buffers() {
+    const int M = cfg_.n_mu, mb = cfg_.mb_rows;
+    act_ld_.resize(L_ + 1);
+    act_ld_[0] = round_up(L_ > 0 ? cfg_.layers[0].in : cfg_.in_dim, 8);
+    for (int l = 1; l <= L_; ++l) act_ld_[l] = round_up(cfg_.layers[l - 1].out, 8);
+    auto dalloc = [&](size_t floats) {
+        float* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(floats, 64) * sizeof(float)));
+        CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(floats, 64) * sizeof(float)));
+        owned_.push_back(p);
+        return p;
+    };
+    // stage input of all micro-batches is ONE buffer so a step needs a single (2-D) copy
+    x_stage_ = dalloc((size_t)M * mb * act_ld_[0]);
+    y_ld_ = round_up(cfg_.out_dim, 8);
+    y_stage_ = dalloc((size_t)M * mb * y_ld_);
+    loss_dev_ = dalloc(std::max(M, 16));
+    CUDA_CHECK(cudaMallocHost(&loss_host_, sizeof(float) * std::max(M, 16)));
+    for (int i = 0; i < std::max(M, 16); ++i) loss_host_[i] = 0.f;
+    {
+        int* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, 64));
+        CUDA_CHECK(cudaMemset(p, 0, 64));
+        owned_.push_back(p);
+        correct_dev_ = p;
+    }
+    act_.assign(M, std::vector<float*>(L_ + 1, nullptr));
+    dz_.assign(M, std::vector<float*>(L_ + 1, nullptr));
+    probs_.assign(M, nullptr);
+    for (int mu = 0; mu < M; ++mu) {
+        act_[mu][0] = x_stage_ + (size_t)mu * mb * act_ld_[0];
+        for (int l = 1; l <= L_; ++l) act_[mu][l] = dalloc((size_t)mb * act_ld_[l]);
+        if (cfg_.training)
+            for (int l = 0; l <= L_; ++l) dz_[mu][l] = dalloc((size_t)mb * act_ld_[l]);
+        probs_[mu] = dalloc((size_t)mb * act_ld_[L_]);
+    }
+}
+
+int PipeEngine::new_event() {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    events_.push_back(e);
+    return (int)events_.size() - 1;
+}
+void PipeEngine::emit_wait(int stream, int ev) {
+    Op op;
+    op.kind = OP_WAIT; op.stream = stream; op.event = ev;
+    ops_.push_back(op);
+}
+int PipeEngine::emit_record(int stream) {
+    Op op;
+    op.kind = OP_RECORD; op.stream = stream; op.event = new_event();
+    ops_.push_back(op);
+    return op.event;
+}
+
+void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
+    if (built_) throw std::runtime_error("PipeEngine::build called twice");
+    const int M = cfg_.n_mu, mb = cfg_.mb_rows, n = (int)instrs.size();
+    const bool first = cfg_.is_first, last = cfg_.is_last;
+
+    // ---- resolve which micro-batch every comm instruction carries
+    std::vector<int> mu_of(n, -1);
+    for (int i = 0; i < n; ++i) {
+        const int op = std::get<0>(instrs[i]), b = std::get<1>(instrs[i]);
+        if (op == I_RECV_ACT || op == I_RECV_GRAD) {
+            for (int j = i + 1; j < n; ++j) {
+                const int oj = std::get<0>(instrs[j]);
+                const bool match = (op == I_RECV_ACT) ? (oj == I_FORWARD) : (oj == I_BWD_ACC || oj == I_BWD_AR);
+                if (match && std::get<1>(instrs[j]) == b) { mu_of[i] = std::get<2>(instrs[j]); break; }
+            }
+        } else if (op == I_SEND_ACT || op == I_SEND_GRAD) {
+            for (int j = i - 1; j >= 0; --j) {
+                const int oj = std::get<0>(instrs[j]);
+                const bool match = (op == I_SEND_ACT) ? (oj == I_FORWARD) : (oj == I_BWD_ACC || oj == I_BWD_AR);
+                if (match && std::get<1>(instrs[j]) == b) { mu_of[i] = std::get<2>(instrs[j]); break; }
+            }
+        } else {
+            mu_of[i] = std::get<2>(instrs[i]);
+        }
+        if ((op >= I_RECV_ACT && op <= I_SEND_GRAD) && mu_of[i] < 0)
+            throw std::runtime_error("PipeEngine: cannot resolve the micro-batch of a comm instruction");
+        if (mu_of[i] >= M) throw std::runtime_error("PipeEngine: micro-batch id out of range");
+    }
+
+    std::vector<bool> started(streams_.size(), false);
+    started[0] = true;
+    Op begin;
+    begin.kind = OP_RECORD; begin.stream = 0; begin.event = new_event();
+    ops_.push_back(begin);
+    const int ev_begin = begin.event;
+    auto use = [&](int s) {
+        if (!started[s]) { emit_wait(s, ev_begin); started[s] = true; }
+    };
+    auto sm = [&](int mu) { return 1 + (mu % n_mu_streams_); };
+    auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
+
+    std::vector<int> ev_in(M, -1), ev_fwd(M, -1), ev_gout(M, -1), ev_bwd(M, -1);
+    std::vector<bool> first_write(L_ + 1, true);
+    std::vector<bool> sw_joined(streams_.size(), false);
+    std::vector<int> ev_allreduce;
+    auto add_gemm = [&](const GemmPlan& g, int stream, int layer, int mu) {
+        gemms_.push_back(g);
+        Op op;
+        op.kind = OP_GEMM; op.stream = stream; op.gemm = (int)gemms_.size() - 1; op.layer = layer; op.mu = mu;
+        ops_.push_back(op);
+    };
+    auto check = [](const char* err) { if (err) throw std::runtime_error(std::string("PipeEngine plan: ") + err); };
+    auto Wl = [&](int l) { return W_ + cfg_.layers[l - 1].offset; };
+    auto Gl = [&](int l) { return G_ + cfg_.layers[l - 1].offset; };
+
+    for (int i = 0; i < n;) {
+        const int opc = std::get<0>(instrs[i]);
+        // ------------------------------------------------ communication group
+        if (opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
+            Op grp;
+            grp.kind = OP_COMM_GROUP; grp.stream = s_comm_;
+            std::vector<std::pair<int, int>> recvs;  // (mu, is_act)
+            use(s_comm_);
+            int j = i;
+            for (; j < n; ++j) {
+                const int o = std::get<0>(instrs[j]);
+                if (!(o >= I_RECV_ACT && o <= I_SEND_GRAD)) break;
+                const int mu = mu_of[j];
+                CommItem it{};
+                if (o == I_SEND_ACT) {
+                    it = {1, cfg_.stage + 1, act_[mu][L_], (size_t)mb * act_ld_[L_]};
+                    if (ev_fwd[mu] >= 0) emit_wait(s_comm_, ev_fwd[mu]);
+                } else if (o == I_RECV_ACT) {
+                    it = {0, cfg_.stage - 1, act_[mu][0], (size_t)mb * act_ld_[0]};
+                    recvs.push_back({mu, 1});
+                } else if (o == I_SEND_GRAD) {
+                    it = {1, cfg_.stage - 1, dz_[mu][0], (size_t)mb * act_ld_[0]};
+                    if (ev_bwd[mu] >= 0) emit_wait(s_comm_, ev_bwd[mu]);
+                } else {
+                    it = {0, cfg_.stage + 1, dz_[mu][L_], (size_t)mb * act_ld_[L_]};
+                    recvs.push_back({mu, 0});
+                }
+                grp.comm.push_back(it);
+            }
+            ops_.push_back(grp);
+            if (!recvs.empty()) {
+                const int ev = emit_record(s_comm_);
+                for (auto& r : recvs) (r.second ? ev_in : ev_gout)[r.first] = ev;
+            }
+            i = j;
+            continue;
+        }
+        const int mu = mu_of[i];
+        switch (opc) {
+            case I_ZERO_GRAD:
+                std::fill(first_write.begin(), first_write.end(), true);
+                break;
+            case I_LOAD_X:
+            case I_LOAD_Y:
+                break;   // the whole DP-local batch is staged with one copy before the step
+            case I_FORWARD: {
+                const int s = sm(mu);
+                use(s);
+                if (ev_in[mu] >= 0) { emit_wait(s, ev_in[mu]); ev_in[mu] = -1; }
+                for (int l = 1; l <= L_; ++l) {
+                    const LayerSpec& ls = cfg_.layers[l - 1];
+                    GemmPlan g;
+                    check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_[mu][l - 1], act_ld_[l - 1], act_[mu][l], act_ld_[l], mb,
+                                        ls.in, ls.out, Wl(l) + ls.in, ls.ld, ls.relu));
+                    add_gemm(g, s, l, mu);
+                }
+                if (!cfg_.training && last) {
+                    Op sm_op;
+                    sm_op.kind = OP_SOFTMAX; sm_op.stream = s;
+                    sm_op.a = act_[mu][L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_[mu]; sm_op.ldb = act_ld_[L_];
+                    sm_op.rows = mb; sm_op.cols = cfg_.out_dim;
+                    ops_.push_back(sm_op);
+                    Op am;
+                    am.kind = OP_ARGMAX; am.stream = s;
+                    am.a = probs_[mu]; am.lda = act_ld_[L_]; am.b = y_stage_ + (size_t)mu * mb * y_ld_; am.ldb = y_ld_;
+                    am.rows = mb; am.cols = cfg_.out_dim;
+                    ops_.push_back(am);
+                }
+                ev_fwd[mu] = emit_record(s);
+                break;
+            }
+            case I_BWD_ACC:
+            case I_BWD_AR: {
+                const bool final_bwd = (opc == I_BWD_AR);
+                const int s = sm(mu);
+                use(s);
+                if (ev_gout[mu] >= 0) { emit_wait(s, ev_gout[mu]); ev_gout[mu] = -1; }
+                if (last) {
+                    Op lh;
+                    lh.kind = OP_LOSS_HEAD; lh.stream = s;
+                    lh.a = act_[mu][L_]; lh.lda = act_ld_[L_];
+                    lh.b = y_stage_ + (size_t)mu * mb * y_ld_; lh.ldb = y_ld_;
+                    lh.c = probs_[mu]; lh.ldc = act_ld_[L_];
+                    lh.d = dz_[mu][L_]; lh.ldd = act_ld_[L_];
+                    lh.rows = mb; lh.cols = cfg_.out_dim; lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = mu;
+                    ops_.push_back(lh);
+                } else if (L_ > 0 && cfg_.layers[L_ - 1].relu) {
+                    Op rm;
+                    rm.kind = OP_RELU_MASK; rm.stream = s;
+                    rm.a = dz_[mu][L_]; rm.lda = act_ld_[L_]; rm.b = act_[mu][L_]; rm.ldb = act_ld_[L_];
+                    rm.rows = mb; rm.cols = cfg_.layers[L_ - 1].out;
+                    ops_.push_back(rm);
+                }
+                const bool defer = final_bwd && cfg_.dp_mode != 1;   // weight-updating wgrads run after every W reader
+                std::vector<std::pair<int, int>> deferred;           // (layer, dz-ready event)
+                for (int l = L_; l >= 1; --l) {
+                    const LayerSpec& ls = cfg_.layers[l - 1];
+                    const int ev_dz = emit_record(s);
+                    if (defer) {
+                        deferred.push_back({l, ev_dz});
+                    } else {
+                        const int w = sw(l);
+                        use(w);
+                        emit_wait(w, ev_dz);
+                        GemmPlan g;
+                        check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
+                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                        add_gemm(g, w, l, mu);
+                        first_write[l] = false;
+                        if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
+                            const int ev_g = emit_record(w);
+                            use(s_dp_);
+                            emit_wait(s_dp_, ev_g);
+                            Op ar;
+                            ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
+                            ops_.push_back(ar);
+                        }
+                    }
+                    if (l > 1 || !first) {
+                        const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
+                        GemmPlan g;
+                        check(gemm_plan_dgrad(&g, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
+                                              ls.out, mask, act_ld_[l - 1]));
+                        add_gemm(g, s, l, mu);
+                    }
+                }
+                ev_bwd[mu] = emit_record(s);
+                if (defer) {
+                    for (auto& d : deferred) {
+                        const int l = d.first;
+                        const LayerSpec& ls = cfg_.layers[l - 1];
+                        const int w = sw(l);
+                        use(w);
+                        if (!sw_joined[w]) {   // every reader of W (fwd/dgrad of all micro-batches) must be done
+                            for (int m2 = 0; m2 < M; ++m2)
+                                if (ev_bwd[m2] >= 0) emit_wait(w, ev_bwd[m2]);
+                                else if (ev_fwd[m2] >= 0) emit_wait(w, ev_fwd[m2]);
+                            sw_joined[w] = true;
+                        }
+                        emit_wait(w, d.second);
+                        GemmPlan g;
+                        if (cfg_.dp_mode == 0) {
+                            check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
+                                                  ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, Wl(l), ls.ld,
+                                                  cfg_.lr, 1));
+                            add_gemm(g, w, l, mu);
+                        } else {
+                            throw std::runtime_error("PipeEngine: fused DP mode is wired by build_fused (not available)");
+                        }
+                        first_write[l] = false;
+                    }
+                }
+                break;
+            }
+            case I_OPT_STEP: {
+                if (cfg_.dp_mode == 1) {
+                    use(s_dp_);
+                    for (int m2 = 0; m2 < M; ++m2)
+                        if (ev_bwd[m2] >= 0) emit_wait(s_dp_, ev_bwd[m2]);
+                    for (int w = 0; w < n_w_streams_; ++w) {
+                        const int ws = 1 + n_mu_streams_ + w;
+                        if (started[ws]) { const int e = emit_record(ws); emit_wait(s_dp_, e); }
+                    }
+                    Op sg;
+                    sg.kind = OP_SGD; sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
+                    ops_.push_back(sg);
+                }
+                break;
+            }
+            default:
+                throw std::runtime_error("PipeEngine: unknown opcode");
+        }
+        ++i;
+    }
+    // ---- join every side stream back into the main stream
+    for (size_t s = 1; s < streams_.size(); ++s)
+        if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
+    if (cfg_.training && last) {
+        Op cp;
+        cp.kind = OP_MEMCPY_LOSS; cp.stream = 0;
+        ops_.push_back(cp);
+    }
+    kernels_per_step_ = 0;
+    for (auto& op : ops_) {
+        if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
+            op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP)
+            ++kernels_per_step_;
+    }
+    built_ = true;
+
+    // kernel attributes are configured up front (never inside a capture); communicators are
+    // warmed up by their creator.  No eager pass here: a training step mutates the weights.
+    CUDA_CHECK(gemm_configure());
+    if (cfg_.use_graph) {
+        CUDA_CHECK(cudaStreamBeginCapture(streams_[0], cudaStreamCaptureModeThreadLocal));
+        walk(true);
+        CUDA_CHECK(cudaStreamEndCapture(streams_[0], &graph_));
+        CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+        size_t nn = 0;
+        CUDA_CHECK(cudaGraphGetNodes(graph_, nullptr, &nn));
+        graph_nodes_ = (int64_t)nn;
+    }
+}
+
+void PipeEngine::exec(const Op& op) {
+    cudaStream_t st = streams_[op.stream];
+    switch (op.kind) {
+        case OP_WAIT: CUDA_CHECK(cudaStreamWaitEvent(st, events_[op.event], 0)); break;
+        case OP_RECORD: CUDA_CHECK(cudaEventRecord(events_[op.event], st)); break;
+        case OP_GEMM: CUDA_CHECK(gemm_launch(gemms_[op.gemm], st)); break;
+        case OP_LOSS_HEAD:
+            CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, loss_dev_ + op.mu, op.rows,
+                                        op.cols, op.scalar, st));
+            break;
+        case OP_SOFTMAX:
+            CUDA_CHECK(launch_loss_head(op.a, op.lda, nullptr, 0, op.b, op.ldb, nullptr, 0, nullptr, op.rows, op.cols, 0.f, st));
+            break;
+        case OP_ARGMAX:
+            CUDA_CHECK(launch_argmax_correct(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, correct_dev_, st));
+            break;
+        case OP_RELU_MASK: CUDA_CHECK(launch_relu_mask(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, st)); break;
+        case OP_SGD: CUDA_CHECK(launch_sgd(op.a, op.b, op.scalar, op.n, st)); break;
+        case OP_ALLREDUCE:
+            if (!dp_comm_) throw std::runtime_error("PipeEngine: DP all-reduce without a communicator");
+            NCCL_CHECK(ncclAllReduce(op.a, op.a, (size_t)op.n, ncclFloat, ncclSum, dp_comm_, st));
+            break;
+        case OP_COMM_GROUP: {
+            if (!pp_comm_) throw std::runtime_error("PipeEngine: pipeline send/recv without a communicator");
+            NCCL_CHECK(ncclGroupStart());
+            for (const auto& it : op.comm) {
+                if (it.is_send) NCCL_CHECK(ncclSend(it.ptr, it.count, ncclFloat, it.peer, pp_comm_, st));
+                else NCCL_CHECK(ncclRecv(it.ptr, it.count, ncclFloat, it.peer, pp_comm_, st));
+            }
+            NCCL_CHECK(ncclGroupEnd());
+            break;
+        }
+        case OP_MEMCPY_LOSS:
+            CUDA_CHECK(cudaMemcpyAsync(loss_host_, loss_dev_, sizeof(float) * cfg_.n_mu, cudaMemcpyDeviceToHost, st));
+            break;
+        default: throw std::runtime_error("PipeEngine: bad op");
+    }
+}
+
+void PipeEngine::walk(bool) {
+    for (const auto& op : ops_) exec(op);
+}
+
+void PipeEngine::stage_inputs(const float* x, const float* y, bool from_host) {
+    const size_t rows = (size_t)cfg_.n_mu * cfg_.mb_rows;
+    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (x != nullptr && cfg_.is_first)
+        CUDA_CHECK(cudaMemcpy2DAsync(x_stage_, (size_t)act_ld_[0] * 4, x, (size_t)cfg_.in_dim * 4, (size_t)cfg_.in_dim * 4, rows,
+                                     kind, streams_[0]));
+    if (y != nullptr && cfg_.is_last)
+        CUDA_CHECK(cudaMemcpy2DAsync(y_stage_, (size_t)y_ld_ * 4, y, (size_t)cfg_.out_dim * 4, (size_t)cfg_.out_dim * 4, rows,
+                                     kind, streams_[0]));
+}
+
+void PipeEngine::run() {
+    if (!built_) throw std::runtime_error("PipeEngine::run before build");
+    if (graph_exec_) CUDA_CHECK(cudaGraphLaunch(graph_exec_, streams_[0]));
+    else walk(false);
+}
+
+void PipeEngine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(streams_[0])); }
+
+float PipeEngine::last_loss() {
+    synchronize();
+    float s = 0.f;
+    for (int i = 0; i < cfg_.n_mu; ++i) s += loss_host_[i];
+    return s;
+}
+
+int PipeEngine::count_correct() {
+    int v = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&v, correct_dev_, sizeof(int), cudaMemcpyDeviceToHost, streams_[0]));
+    synchronize();
+    return v;
+}
+void PipeEngine::reset_correct() { CUDA_CHECK(cudaMemsetAsync(correct_dev_, 0, sizeof(int), streams_[0])); }
+
+std::string PipeEngine::describe() const {
+    std::ostringstream os;
+    os << "PipeEngine(stage " << cfg_.stage << "/" << cfg_.n_stages << ", layers=" << L_ << ", mb_rows=" << cfg_.mb_rows
+       << ", n_mu=" << cfg_.n_mu << ", ops=" << ops_.size() << ", kernels/step=" << kernels_per_step_
+       << ", graph_nodes=" << graph_nodes_ << ", streams=" << streams_.size() << ", events=" << events_.size() << ")";
+    return os.str();
+}
+
+}  // namespace ssb

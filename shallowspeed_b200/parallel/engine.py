@@ -1,0 +1,200 @@
+"""Python face of the native pipeline executor (``csrc/runtime/pipe_engine.cpp``).
+
+``NativeWorker`` has the surface of the reference's ``Worker`` (``execute(sched,
+batch_id)``, ``output_buffers``, ``stage_id``, ``pipeline_depth``; pipe.py:330-466) but
+lowers each distinct schedule ONCE into a static CUDA-graph plan and replays it.
+
+``Trainer`` is the user-facing end-to-end API (``trainer.step(x_host, y_host) -> loss``):
+inputs come from pinned host memory, one H2D copy per step, loss read back per step.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .comm import Comm, ProcessGrid, SelfComm, TorchComm
+from .instructions import encode, flatten
+from .schedules import InferenceSchedule, Schedule
+from .validate import simulate
+
+DP_MODE = {"none": 0, "nccl": 1, "fused": 2}
+
+
+def _C():
+    from .. import _C as mod
+
+    return mod
+
+
+def make_nccl_comm(comm: Comm):
+    """Create a native ncclComm for the ranks of a ``TorchComm`` (unique id travels over
+    torch.distributed).  Returns None for size-1 communicators."""
+    if comm is None or comm.Get_size() == 1:
+        return None
+    assert isinstance(comm, TorchComm), "native engine needs torch.distributed (NCCL) communicators"
+    import torch.distributed as dist
+
+    box = [_C().NcclComm.unique_id() if comm.rank == 0 else None]
+    dist.broadcast_object_list(box, src=comm.ranks[0], group=comm.group)
+    nc = _C().NcclComm(box[0], comm.size, comm.rank)
+    nc.warmup()
+    return nc
+
+
+class NativeWorker:
+    def __init__(self, dp_comm, pp_comm, model, dataset, optimizer, grid: Optional[ProcessGrid] = None,
+                 comm_mode: str = "fused", use_graph: bool = True, precision: str = "tf32", share=None,
+                 validate_schedules: bool = True):
+        self.dp_comm = dp_comm if dp_comm is not None else SelfComm()
+        self.pp_comm = pp_comm if pp_comm is not None else SelfComm()
+        self.stage_id = self.pp_comm.Get_rank()
+        self.pipeline_depth = self.pp_comm.Get_size()
+        self.model, self.dataset, self.optimizer = model, dataset, optimizer
+        self.use_graph, self.precision = use_graph, precision
+        self.validate_schedules = validate_schedules
+        self.device = model.arena.weights.device
+        assert self.device.type == "cuda", "NativeWorker needs the model on a CUDA device (model.to('cuda'))"
+        if self.dp_comm.Get_size() == 1:
+            self.dp_mode = "none"
+        else:
+            self.dp_mode = comm_mode
+        # native communicators are shared between the train and the validation worker
+        if share is not None:
+            self._pp_nccl, self._dp_nccl = share._pp_nccl, share._dp_nccl
+        else:
+            self._pp_nccl = make_nccl_comm(self.pp_comm)
+            self._dp_nccl = make_nccl_comm(self.dp_comm) if dp_comm is not None else None
+        self._engines = {}
+        self._last_engine = None
+        self.lr = optimizer.lr if optimizer is not None else 0.0
+
+    # ------------------------------------------------------------------ plan cache
+    def _key(self, sched: Schedule):
+        return (type(sched).__name__, sched.num_micro_batches, sched.num_stages, sched.stage_id,
+                self.dataset.mubatch_size)
+
+    def _build(self, sched: Schedule):
+        if self.validate_schedules:   # prove the whole pipeline deadlock-free before touching the GPU
+            simulate([type(sched)(sched.num_micro_batches, sched.num_stages, s) for s in range(sched.num_stages)])
+        m = self.model
+        specs = []
+        for lin in m.linears:
+            specs.append((lin.in_dims, lin.out_dims, 1 if lin.activation is not None else 0,
+                          int(m.arena.offsets[lin.block_index]), int(m.arena.lds[lin.block_index])))
+        training = bool(sched.training)
+        cfg = dict(is_first=int(sched.is_first_stage), is_last=int(sched.is_last_stage), stage=sched.stage_id,
+                   n_stages=sched.num_stages, mb_rows=self.dataset.mubatch_size, n_mu=sched.num_micro_batches,
+                   global_batch=m.batch_size, lr=float(self.lr), training=int(training), use_graph=int(self.use_graph),
+                   dp_size=self.dp_comm.Get_size(), dp_rank=self.dp_comm.Get_rank(),
+                   dp_mode=DP_MODE[self.dp_mode] if training else 0, in_dim=m.in_dim, out_dim=m.out_dim)
+        eng = _C().PipeEngine(specs, cfg, m.arena.weights, m.arena.grads)
+        if self._pp_nccl is not None:
+            eng.set_pp_comm(self._pp_nccl)
+        if self._dp_nccl is not None and training:
+            eng.set_dp_comm(self._dp_nccl)
+        torch.cuda.synchronize(self.device)
+        eng.build([encode(i) for i in flatten(list(sched.steps()))])
+        return eng
+
+    def engine_for(self, sched: Schedule):
+        key = self._key(sched)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = self._build(sched)
+        return eng
+
+    # ------------------------------------------------------------------ Worker surface
+    def execute(self, sched: Schedule, batch_id: int):
+        eng = self.engine_for(sched)
+        x, y = self.dataset.load_batch(batch_id)
+        eng.stage_inputs(x if sched.is_first_stage else None, y if sched.is_last_stage else None)
+        eng.run()
+        self._last_engine = eng
+
+    def step_from(self, sched: Schedule, x, y):
+        """Run one step on explicit (pinned-host or device) batch tensors."""
+        eng = self.engine_for(sched)
+        eng.stage_inputs(x if sched.is_first_stage else None, y if sched.is_last_stage else None)
+        eng.run()
+        self._last_engine = eng
+        return eng
+
+    @property
+    def output_buffers(self):
+        """Inference: softmax output of micro-batch 0 on the last stage (train.py reads
+        ``worker.output_buffers[0]``)."""
+        eng = self._last_engine
+        eng.synchronize()
+        n_mu = 1
+        return [eng.probs(mu) for mu in range(n_mu)]
+
+    def batch_loss(self):
+        if self._last_engine is None or self.stage_id != self.pipeline_depth - 1:
+            return None
+        return float(self._last_engine.last_loss())
+
+    def synchronize(self):
+        for e in self._engines.values():
+            e.synchronize()
+
+    def sync_to_model(self):
+        """Weights live in the model's arena already; just drain the streams."""
+        self.synchronize()
+        torch.cuda.synchronize(self.device)
+
+    def kernels_per_step(self, sched):
+        return int(self.engine_for(sched).kernels_per_step())
+
+    def describe(self, sched):
+        return self.engine_for(sched).describe()
+
+
+class Trainer:
+    """End-to-end training API: the call a user makes.
+
+        trainer = Trainer(layer_sizes, dp=1, pp=1, schedule="naive", ...)
+        loss = trainer.step(x_host, y_host)        # pinned host tensors of the DP-local batch
+
+    Every step copies its inputs host->device and reads its loss device->host.
+    """
+
+    def __init__(self, layer_sizes, global_batch_size=128, n_mubatches=4, lr=0.006, schedule="naive",
+                 dp_comm=None, pp_comm=None, grid: Optional[ProcessGrid] = None, comm_mode="fused",
+                 use_graph=True, device=None, seed_mode="shape"):
+        from ..models.mlp import MLP
+        from ..optimizer import SGD
+        from .schedules import SCHEDULE_NAME_TO_CLS
+
+        self.dp_comm = dp_comm if dp_comm is not None else SelfComm()
+        self.pp_comm = pp_comm if pp_comm is not None else SelfComm()
+        dp, pp = self.dp_comm.Get_size(), self.pp_comm.Get_size()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.global_batch_size, self.n_mubatches = global_batch_size, n_mubatches
+        self.local_batch_size = global_batch_size // dp
+        self.model = MLP(layer_sizes, self.pp_comm.Get_rank(), pp, global_batch_size, seed_mode=seed_mode).to(self.device)
+        self.optimizer = SGD(self.model.parameters(), lr, arena=self.model.arena)
+
+        class _Shape:  # the worker only needs the micro-batch size from the dataset
+            mubatch_size = self.local_batch_size // n_mubatches
+
+        self.worker = NativeWorker(dp_comm, pp_comm, self.model, _Shape(), self.optimizer, grid=grid,
+                                   comm_mode=comm_mode, use_graph=use_graph)
+        cls = SCHEDULE_NAME_TO_CLS[schedule] if isinstance(schedule, str) else schedule
+        self.schedule = cls(n_mubatches, pp, self.pp_comm.Get_rank())
+        self.engine = self.worker.engine_for(self.schedule)
+        self.is_first, self.is_last = self.schedule.is_first_stage, self.schedule.is_last_stage
+
+    def step_async(self, x_host, y_host):
+        self.engine.stage_inputs(x_host if self.is_first else None, y_host if self.is_last else None)
+        self.engine.run()
+
+    def step(self, x_host, y_host):
+        self.step_async(x_host, y_host)
+        return self.engine.last_loss() if self.is_last else None
+
+    def loss(self):
+        return self.engine.last_loss() if self.is_last else None
+
+    def synchronize(self):
+        self.engine.synchronize()
