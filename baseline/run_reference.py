@@ -32,7 +32,7 @@ def main(argv=None):
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--global-batch-size", type=int, default=128)
     ap.add_argument("--n-mubatches", type=int, default=4)
-    ap.add_argument("--data-dir", default=str(HERE / "_ref" / "data" / "mnist_784"))
+    ap.add_argument("--data-dir", default="/tmp/ssb_ref_data/mnist_784")
     ap.add_argument("--keep-fp64", action="store_true", help="do not cast the weights back to fp32")
     ap.add_argument("--threads", type=int, default=0, help="BLAS threads per rank (0 = cores / ranks)")
     args = ap.parse_args(argv)

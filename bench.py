@@ -70,7 +70,10 @@ def run_reference(args):
         return
     rank = int(os.environ.get("RANK", "0"))
     gbs = global_batch(args)
-    data_dir = os.path.join(ROOT, "baseline", "_ref", "data", "mnist_784")
+    import tempfile
+
+    # generated on the box (10 s) instead of shipping 200 MB of parquet with every snapshot
+    data_dir = os.path.join(tempfile.gettempdir(), "ssb_ref_data", "mnist_784")
     if rank == 0:
         from shallowspeed_b200.dataset import write_reference_files
 

@@ -42,9 +42,18 @@ __global__ void __launch_bounds__(256) loss_head_kernel(const float* __restrict_
                                                         const float* __restrict__ aux, int lda,   // target | upstream
                                                         float* __restrict__ probs, int ldp,
                                                         float* __restrict__ dlogits, int ldd,
-                                                        float* __restrict__ loss_out, int rows, int cols, float inv_batch) {
+                                                        float* __restrict__ loss_out, int rows_total, int cols, float inv_batch,
+                                                        int rows_per_block) {
+    // one CTA per micro-batch: the global-max / loss contract is per micro-batch
     __shared__ float scratch[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int row0 = blockIdx.x * rows_per_block;
+    const int rows = min(rows_per_block, rows_total - row0);
+    logits += (size_t)row0 * ldl;
+    if (aux != nullptr) aux += (size_t)row0 * lda;
+    if (probs != nullptr) probs += (size_t)row0 * ldp;
+    if (dlogits != nullptr) dlogits += (size_t)row0 * ldd;
+    if (loss_out != nullptr) loss_out += blockIdx.x;
 
     float mx = -FLT_MAX;
     for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) mx = fmaxf(mx, logits[(size_t)(i / cols) * ldl + (i % cols)]);
@@ -86,17 +95,19 @@ __global__ void __launch_bounds__(256) loss_head_kernel(const float* __restrict_
 
 cudaError_t launch_loss_head(const float* logits, int ldl, const float* target, int ldt, float* probs, int ldp,
                              float* dlogits, int ldd, float* loss_out, int rows, int cols, float inv_batch,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int rows_per_mubatch) {
+    const int rpb = rows_per_mubatch > 0 ? rows_per_mubatch : rows;
+    const int blocks = (rows + rpb - 1) / rpb;
     if (target != nullptr)
-        loss_head_kernel<1><<<1, 256, 0, stream>>>(logits, ldl, target, ldt, probs, ldp, dlogits, ldd, loss_out, rows, cols, inv_batch);
+        loss_head_kernel<1><<<blocks, 256, 0, stream>>>(logits, ldl, target, ldt, probs, ldp, dlogits, ldd, loss_out, rows, cols, inv_batch, rpb);
     else
-        loss_head_kernel<0><<<1, 256, 0, stream>>>(logits, ldl, nullptr, 0, probs, ldp, nullptr, 0, nullptr, rows, cols, 0.f);
+        loss_head_kernel<0><<<blocks, 256, 0, stream>>>(logits, ldl, nullptr, 0, probs, ldp, nullptr, 0, nullptr, rows, cols, 0.f, rpb);
     return cudaGetLastError();
 }
 
 cudaError_t launch_softmax_grad(const float* logits, int ldl, const float* upstream, int ldu, float* dlogits, int ldd,
                                 int rows, int cols, cudaStream_t stream) {
-    loss_head_kernel<2><<<1, 256, 0, stream>>>(logits, ldl, upstream, ldu, nullptr, 0, dlogits, ldd, nullptr, rows, cols, 0.f);
+    loss_head_kernel<2><<<1, 256, 0, stream>>>(logits, ldl, upstream, ldu, nullptr, 0, dlogits, ldd, nullptr, rows, cols, 0.f, rows);
     return cudaGetLastError();
 }
 

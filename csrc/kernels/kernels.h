@@ -35,7 +35,8 @@ struct GemmParams {
     int accumulate;
     float* db;          // nullable
     int db_stride;
-    // WGRAD with the SGD update fused (single replica): W -= lr * (G_prev + D); G untouched
+    // WGRAD with the SGD update fused (single replica, not combinable with accumulate):
+    // the -lr-scaled tile is TMA-reduce-added into W; G is never touched
     float* W;
     int ldw;
     float lr;
@@ -43,7 +44,7 @@ struct GemmParams {
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;   // C: WGRAD output tile (G, or W when the SGD update is fused)
     GemmParams p;
     int mode;
     dim3 grid;
@@ -71,7 +72,7 @@ int gemm_kernel_count();   // number of launches issued so far by this module (b
 // grad, 1/batch_size inside) and loss_out[0] = sum((t-p)^2)/batch_size.
 cudaError_t launch_loss_head(const float* logits, int ldl, const float* target, int ldt, float* probs, int ldp,
                              float* dlogits, int ldd, float* loss_out, int rows, int cols, float inv_batch,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int rows_per_mubatch = 0);   // >0: one CTA per micro-batch, loss_out[mu]
 // generic softmax backward for the functional API: dz = p*up - p*sum(p*up)
 cudaError_t launch_softmax_grad(const float* logits, int ldl, const float* upstream, int ldu, float* dlogits, int ldd,
                                 int rows, int cols, cudaStream_t stream);

@@ -32,7 +32,8 @@ static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     constexpr bool A_MN = (MODE != GEMM_FWD);
     constexpr bool B_MN = (MODE == GEMM_WGRAD);
 
@@ -47,13 +48,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
     const uint32_t b_bytes = p.block_n * 128u;
     const uint32_t stage_bytes = kABytes + b_bytes;
-    const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+    // WGRAD stages its output tile (block_n/32 swizzled panels of [128 rows x 128 B]) behind the ring
+    const uint32_t epi_base = smem_base + p.stages * stage_bytes;
+    const uint32_t epi_bytes = (MODE == GEMM_WGRAD) ? (uint32_t)p.block_n * 512u : 0u;
+    const uint32_t bar_base = epi_base + epi_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
     const uint32_t tmem_slot = tmem_full_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + 8u * (2 * p.stages) + 8u);
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + epi_bytes + 8u * (2 * p.stages) + 8u);
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
@@ -63,6 +67,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (MODE == GEMM_WGRAD) tma_prefetch_desc(&tmC);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), db_active ? 5 : 1);   // MMA commit (+ 4 db-reducing warps)
@@ -161,71 +166,85 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
         if (MODE == GEMM_FWD || MODE == GEMM_DGRAD) {
             float bias = 0.f;
-            if (MODE == GEMM_FWD && p.bias != nullptr && m_ok) bias = p.bias[(size_t)m * p.bias_stride];
+            if (MODE == GEMM_FWD && p.bias != nullptr && m_ok) bias = __ldg(p.bias + (size_t)m * p.bias_stride);
+            const float* __restrict__ mask = p.mask;
+            float* __restrict__ out = p.out;
             for (int c = 0; c < p.block_n; c += 16) {
+                float mk[16];
+                if (MODE == GEMM_DGRAD && mask != nullptr && m_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {       // all 16 loads in flight before any use
+                        const int n = n0 + c + j;
+                        mk[j] = (n < p.n_total) ? __ldg(mask + (size_t)n * p.ldmask + m) : 0.f;
+                    }
+                }
                 float v[16];
                 tmem_ld16(taddr + c, v);
                 if (!m_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c + j;
-                    if (n < p.n_total) {
-                        float x = v[j] + bias;
-                        if (MODE == GEMM_FWD) {
-                            if (p.relu) x = fmaxf(x, 0.f);
-                        } else if (p.mask != nullptr) {
-                            x = (p.mask[(size_t)n * p.ldmask + m] > 0.f) ? x : 0.f;
-                        }
-                        p.out[(size_t)n * p.ldo + m] = x;     // lanes -> consecutive m: coalesced
+                    float x = v[j] + bias;
+                    if (MODE == GEMM_FWD) {
+                        if (p.relu) x = fmaxf(x, 0.f);
+                    } else if (mask != nullptr) {
+                        x = (mk[j] > 0.f) ? x : 0.f;
                     }
+                    v[j] = x;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < p.n_total) out[(size_t)n * p.ldo + m] = v[j];     // lanes -> consecutive m: coalesced
                 }
             }
         } else {
-            for (int c = 0; c < p.block_n; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + c, v);
-                if (!m_ok) continue;
-                const int nb = n0 + c;
-                float* grow = p.G + (size_t)m * p.ldg + nb;
-                float* wrow = p.fuse_sgd ? p.W + (size_t)m * p.ldw + nb : nullptr;
+            // WGRAD: TMEM -> registers -> swizzled smem panels -> ONE TMA store (overwrite) or TMA
+            // reduce-add (accumulate, performed in L2) per 32-column panel.  With fuse_sgd the tile is
+            // scaled by -lr and reduce-added straight into W: dW never touches memory, zero_grad and
+            // the optimizer pass disappear.  OOB rows/columns are clipped by the tensor map, so the
+            // bias column (index n_total of the same [out, ld] block) is never touched here.
+            const float scale = p.fuse_sgd ? -p.lr : 1.f;
+            for (int pj = 0; pj < p.block_n / 32; ++pj) {
+                const uint32_t prow = epi_base + pj * (kBlockM * 128u) + (uint32_t)m_local * 128u;
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const int n = nb + 4 * g4;
-                    if (n + 3 < p.n_total) {
-                        float4 acc = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
-                        if (p.accumulate) {
-                            const float4 o = *reinterpret_cast<const float4*>(grow + 4 * g4);
-                            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-                        }
-                        if (p.fuse_sgd) {
-                            float4 w = *reinterpret_cast<const float4*>(wrow + 4 * g4);
-                            w.x -= p.lr * acc.x; w.y -= p.lr * acc.y; w.z -= p.lr * acc.z; w.w -= p.lr * acc.w;
-                            *reinterpret_cast<float4*>(wrow + 4 * g4) = w;
-                        } else {
-                            *reinterpret_cast<float4*>(grow + 4 * g4) = acc;
-                        }
-                    } else {
+                for (int h = 0; h < 2; ++h) {
+                    float v[16];
+                    tmem_ld16(taddr + pj * 32 + h * 16, v);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (n + e < p.n_total) {
-                                float acc = v[4 * g4 + e];
-                                if (p.accumulate) acc += grow[4 * g4 + e];
-                                if (p.fuse_sgd) wrow[4 * g4 + e] -= p.lr * acc;
-                                else grow[4 * g4 + e] = acc;
-                            }
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t chunk = (uint32_t)(h * 4 + q) ^ ((uint32_t)m_local & 7u);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (chunk << 4)),
+                                     "f"(v[4 * q] * scale), "f"(v[4 * q + 1] * scale), "f"(v[4 * q + 2] * scale),
+                                     "f"(v[4 * q + 3] * scale)
+                                     : "memory");
                     }
                 }
             }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // the 4 epilogue warps only
+            if (warp == 2 && lane == 0) {
+                const bool add = p.accumulate || p.fuse_sgd;
+                for (int pj = 0; pj < p.block_n / 32; ++pj) {
+                    if (n0 + pj * 32 >= p.n_total) break;
+                    const uint32_t src = epi_base + pj * (kBlockM * 128u);
+                    if (add) tma_reduce_add_2d(&tmC, src, n0 + pj * 32, m0);
+                    else tma_store_2d(&tmC, src, n0 + pj * 32, m0);
+                }
+                tma_store_commit();
+                tma_store_wait_all();
+            }
+            // TMA stores clip the inner dimension at 16-byte granularity (measured on B200: with
+            // in % 4 != 0 the partially valid last chunk is written in full), i.e. the bias slot in
+            // column `in` may just have been overwritten with the (zero) accumulator of an OOB
+            // column.  The bias gradient is therefore written strictly AFTER the tile store retired.
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (db_active && m_ok) {
-                float* dbp = p.db + (size_t)m * p.db_stride;
-                float acc = dbsum;
-                if (p.accumulate) acc += *dbp;
                 if (p.fuse_sgd) {
                     float* bp = p.W + (size_t)m * p.ldw + (p.db - p.G);   // bias lives at the same offset in W
-                    *bp -= p.lr * acc;
+                    *bp -= p.lr * dbsum;
                 } else {
-                    *dbp = acc;
+                    float* dbp = p.db + (size_t)m * p.db_stride;
+                    *dbp = p.accumulate ? (*dbp + dbsum) : dbsum;
                 }
             }
         }
@@ -259,7 +278,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 row-major tensor [outer, inner] with pitch ld (floats); box = [box_outer, box_inner=32], SWIZZLE_128B.
 static const char* make_tmap(CUtensorMap* map, const float* base, int inner, int outer, int ld, int box_outer,
-                             bool mn_major = false) {
+                             bool mn_major = false, bool l2_256 = true) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return "cuTensorMapEncodeTiled entry point not available";
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return "TMA: base address must be 16-byte aligned";
@@ -285,12 +304,13 @@ static void finish_plan(GemmPlan* plan) {
     GemmParams& p = plan->p;
     const int num_kb = (p.k_total + (int)kBlockK - 1) / (int)kBlockK;
     const int stage_bytes = (int)kABytes + p.block_n * 128;
-    int stages = 200 * 1024 / stage_bytes;
+    const int epi_bytes = plan->mode == GEMM_WGRAD ? p.block_n * 512 : 0;
+    int stages = (200 * 1024 - epi_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages > num_kb) stages = num_kb;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2) + 16;
+    plan->smem_bytes = stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 8 * (2 * stages + 2) + 16;
     plan->grid = dim3((p.m_total + kBlockM - 1) / kBlockM, (p.n_total + p.block_n - 1) / p.block_n, 1);
 }
 
@@ -304,6 +324,7 @@ const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* 
     p.out = Y; p.ldo = ldy; p.bias = bias; p.bias_stride = bias_stride; p.relu = relu;
     if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, kBlockM)) return e;
     if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, p.block_n)) return e;
+    plan->tmC = plan->tmA;
     finish_plan(plan);
     return nullptr;
 }
@@ -318,6 +339,7 @@ const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float
     p.out = dX; p.ldo = lddx; p.mask = mask; p.ldmask = ldmask;
     if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, 32, true)) return e;          // MN-major panels [32 k x 32 m]
     if (const char* e = make_tmap(&plan->tmB, dZ, out, rows, lddz, p.block_n)) return e;
+    plan->tmC = plan->tmA;
     finish_plan(plan);
     return nullptr;
 }
@@ -333,6 +355,9 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
     p.G = G; p.ldg = ldg; p.accumulate = accumulate; p.db = db; p.db_stride = db_stride;
     p.W = W; p.ldw = ldw; p.lr = lr; p.fuse_sgd = fuse_sgd;
     if (fuse_sgd && W == nullptr) return "fuse_sgd needs W";
+    if (fuse_sgd && accumulate) return "fuse_sgd cannot be combined with accumulate (reduce into G, then run the SGD pass)";
+    // output tile map: [out, in] with the block's row pitch; fused SGD targets W itself
+    if (const char* e = make_tmap(&plan->tmC, fuse_sgd ? W : G, in, out, fuse_sgd ? ldw : ldg, kBlockM)) return e;
     if (const char* e = make_tmap(&plan->tmA, dZ, out, rows, lddz, 32, true)) return e;
     if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, 32, true)) return e;
     finish_plan(plan);
@@ -361,7 +386,7 @@ static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
         cudaError_t e = gemm_configure();
         if (e != cudaSuccess) return e;
     }
-    tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.p);
+    tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

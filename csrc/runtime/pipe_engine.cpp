@@ -3,6 +3,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <sstream>
 #include <stdexcept>
 
@@ -33,6 +34,8 @@ PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, in
     : cfg_(cfg), W_(weights), G_(grads), arena_numel_(arena_numel), L_((int)cfg.layers.size()) {
     n_mu_streams_ = std::max(1, std::min(cfg_.n_mu, 4));
     n_w_streams_ = std::max(1, std::min(L_, 4));
+    if (const char* e = getenv("SSB_MU_STREAMS")) n_mu_streams_ = std::max(1, std::min(atoi(e), std::max(1, cfg_.n_mu)));
+    if (const char* e = getenv("SSB_W_STREAMS")) n_w_streams_ = std::max(1, atoi(e));
     const int n_streams = 1 + n_mu_streams_ + n_w_streams_ + 2;
     s_comm_ = 1 + n_mu_streams_ + n_w_streams_;
     s_dp_ = s_comm_ + 1;
@@ -77,15 +80,25 @@ void PipeEngine::alloc_buffers() {
         owned_.push_back(p);
         correct_dev_ = p;
     }
+    // one contiguous [M * mb, ld] buffer per layer boundary: micro-batch mu owns rows
+    // [mu*mb, (mu+1)*mb).  A stage without pipeline communication runs ALL micro-batches of a
+    // layer in one launch (horizontal fusion); otherwise each micro-batch uses its row slice.
+    act_all_.assign(L_ + 1, nullptr);
+    dz_all_.assign(L_ + 1, nullptr);
+    act_all_[0] = x_stage_;
+    for (int l = 1; l <= L_; ++l) act_all_[l] = dalloc((size_t)M * mb * act_ld_[l]);
+    if (cfg_.training)
+        for (int l = 0; l <= L_; ++l) dz_all_[l] = dalloc((size_t)M * mb * act_ld_[l]);
+    probs_all_ = dalloc((size_t)M * mb * act_ld_[L_]);
     act_.assign(M, std::vector<float*>(L_ + 1, nullptr));
     dz_.assign(M, std::vector<float*>(L_ + 1, nullptr));
     probs_.assign(M, nullptr);
     for (int mu = 0; mu < M; ++mu) {
-        act_[mu][0] = x_stage_ + (size_t)mu * mb * act_ld_[0];
-        for (int l = 1; l <= L_; ++l) act_[mu][l] = dalloc((size_t)mb * act_ld_[l]);
-        if (cfg_.training)
-            for (int l = 0; l <= L_; ++l) dz_[mu][l] = dalloc((size_t)mb * act_ld_[l]);
-        probs_[mu] = dalloc((size_t)mb * act_ld_[L_]);
+        for (int l = 0; l <= L_; ++l) {
+            act_[mu][l] = act_all_[l] + (size_t)mu * mb * act_ld_[l];
+            if (cfg_.training) dz_[mu][l] = dz_all_[l] + (size_t)mu * mb * act_ld_[l];
+        }
+        probs_[mu] = probs_all_ + (size_t)mu * mb * act_ld_[L_];
     }
 }
 
@@ -134,6 +147,18 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         if ((op >= I_RECV_ACT && op <= I_SEND_GRAD) && mu_of[i] < 0)
             throw std::runtime_error("PipeEngine: cannot resolve the micro-batch of a comm instruction");
         if (mu_of[i] >= M) throw std::runtime_error("PipeEngine: micro-batch id out of range");
+    }
+
+    bool has_comm = false;
+    for (int i = 0; i < n; ++i) {
+        const int op = std::get<0>(instrs[i]);
+        if (op >= I_RECV_ACT && op <= I_SEND_GRAD) has_comm = true;
+    }
+    coalesced_ = !has_comm && !getenv("SSB_NO_COALESCE");
+    if (coalesced_) {
+        build_coalesced();
+        finish_build();
+        return;
     }
 
     std::vector<bool> started(streams_.size(), false);
@@ -255,69 +280,38 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
                     rm.rows = mb; rm.cols = cfg_.layers[L_ - 1].out;
                     ops_.push_back(rm);
                 }
-                const bool defer = final_bwd && cfg_.dp_mode != 1;   // weight-updating wgrads run after every W reader
-                std::vector<std::pair<int, int>> deferred;           // (layer, dz-ready event)
                 for (int l = L_; l >= 1; --l) {
                     const LayerSpec& ls = cfg_.layers[l - 1];
                     const int ev_dz = emit_record(s);
-                    if (defer) {
-                        deferred.push_back({l, ev_dz});
-                    } else {
-                        const int w = sw(l);
-                        use(w);
-                        emit_wait(w, ev_dz);
-                        GemmPlan g;
-                        check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
-                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
-                        add_gemm(g, w, l, mu);
-                        first_write[l] = false;
-                        if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
-                            const int ev_g = emit_record(w);
-                            use(s_dp_);
-                            emit_wait(s_dp_, ev_g);
-                            Op ar;
-                            ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
-                            ops_.push_back(ar);
-                        }
+                    const int w = sw(l);
+                    use(w);
+                    emit_wait(w, ev_dz);
+                    GemmPlan g;
+                    check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
+                                          ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                    add_gemm(g, w, l, mu);
+                    first_write[l] = false;
+                    if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
+                        const int ev_g = emit_record(w);
+                        use(s_dp_);
+                        emit_wait(s_dp_, ev_g);
+                        Op ar;
+                        ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
+                        ops_.push_back(ar);
                     }
                     if (l > 1 || !first) {
                         const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
-                        GemmPlan g;
-                        check(gemm_plan_dgrad(&g, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
+                        GemmPlan g2;
+                        check(gemm_plan_dgrad(&g2, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
                                               ls.out, mask, act_ld_[l - 1]));
-                        add_gemm(g, s, l, mu);
+                        add_gemm(g2, s, l, mu);
                     }
                 }
                 ev_bwd[mu] = emit_record(s);
-                if (defer) {
-                    for (auto& d : deferred) {
-                        const int l = d.first;
-                        const LayerSpec& ls = cfg_.layers[l - 1];
-                        const int w = sw(l);
-                        use(w);
-                        if (!sw_joined[w]) {   // every reader of W (fwd/dgrad of all micro-batches) must be done
-                            for (int m2 = 0; m2 < M; ++m2)
-                                if (ev_bwd[m2] >= 0) emit_wait(w, ev_bwd[m2]);
-                                else if (ev_fwd[m2] >= 0) emit_wait(w, ev_fwd[m2]);
-                            sw_joined[w] = true;
-                        }
-                        emit_wait(w, d.second);
-                        GemmPlan g;
-                        if (cfg_.dp_mode == 0) {
-                            check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
-                                                  ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, Wl(l), ls.ld,
-                                                  cfg_.lr, 1));
-                            add_gemm(g, w, l, mu);
-                        } else {
-                            throw std::runtime_error("PipeEngine: fused DP mode is wired by build_fused (not available)");
-                        }
-                        first_write[l] = false;
-                    }
-                }
                 break;
             }
             case I_OPT_STEP: {
-                if (cfg_.dp_mode == 1) {
+                {
                     use(s_dp_);
                     for (int m2 = 0; m2 < M; ++m2)
                         if (ev_bwd[m2] >= 0) emit_wait(s_dp_, ev_bwd[m2]);
@@ -344,6 +338,112 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         cp.kind = OP_MEMCPY_LOSS; cp.stream = 0;
         ops_.push_back(cp);
     }
+    finish_build();
+}
+
+// Stage without pipeline communication (pp == 1): micro-batches are independent until the
+// optimizer step, so every layer runs ONCE over all of them (rows = n_mu * mb_rows).  The
+// loss head still runs one CTA per micro-batch (its global-max contract is per micro-batch),
+// the weight gradient accumulates over the micro-batches in TMEM (k-blocks in micro-batch
+// order) instead of through memory, and with a single replica the SGD update is fused into
+// the wgrad epilogue (TMA reduce-add of -lr * dW into W): ZeroGrad / OptimizerStep vanish.
+void PipeEngine::build_coalesced() {
+    const int M = cfg_.n_mu, mb = cfg_.mb_rows, rows = M * mb;
+    auto check = [](const char* err) { if (err) throw std::runtime_error(std::string("PipeEngine plan: ") + err); };
+    auto Wl = [&](int l) { return W_ + cfg_.layers[l - 1].offset; };
+    auto Gl = [&](int l) { return G_ + cfg_.layers[l - 1].offset; };
+    auto add_gemm = [&](const GemmPlan& g, int stream, int layer) {
+        gemms_.push_back(g);
+        Op op;
+        op.kind = OP_GEMM; op.stream = stream; op.gemm = (int)gemms_.size() - 1; op.layer = layer; op.mu = -1;
+        ops_.push_back(op);
+    };
+    std::vector<bool> started(streams_.size(), false);
+    started[0] = true;
+    Op begin;
+    begin.kind = OP_RECORD; begin.stream = 0; begin.event = new_event();
+    ops_.push_back(begin);
+    const int ev_begin = begin.event;
+    auto use = [&](int s) { if (!started[s]) { emit_wait(s, ev_begin); started[s] = true; } };
+    auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
+
+    for (int l = 1; l <= L_; ++l) {
+        const LayerSpec& ls = cfg_.layers[l - 1];
+        GemmPlan g;
+        check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_all_[l - 1], act_ld_[l - 1], act_all_[l], act_ld_[l], rows, ls.in, ls.out,
+                            Wl(l) + ls.in, ls.ld, ls.relu));
+        add_gemm(g, 0, l);
+    }
+    if (!cfg_.training) {
+        Op sm_op;
+        sm_op.kind = OP_SOFTMAX; sm_op.stream = 0;
+        sm_op.a = act_all_[L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_all_; sm_op.ldb = act_ld_[L_];
+        sm_op.rows = rows; sm_op.cols = cfg_.out_dim; sm_op.n = mb;
+        ops_.push_back(sm_op);
+        Op am;
+        am.kind = OP_ARGMAX; am.stream = 0;
+        am.a = probs_all_; am.lda = act_ld_[L_]; am.b = y_stage_; am.ldb = y_ld_; am.rows = rows; am.cols = cfg_.out_dim;
+        ops_.push_back(am);
+        return;
+    }
+    Op lh;
+    lh.kind = OP_LOSS_HEAD; lh.stream = 0;
+    lh.a = act_all_[L_]; lh.lda = act_ld_[L_]; lh.b = y_stage_; lh.ldb = y_ld_; lh.c = probs_all_; lh.ldc = act_ld_[L_];
+    lh.d = dz_all_[L_]; lh.ldd = act_ld_[L_]; lh.rows = rows; lh.cols = cfg_.out_dim;
+    lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = 0; lh.n = mb;
+    ops_.push_back(lh);
+
+    const bool fuse = (cfg_.dp_mode == 0);
+    std::vector<int> tail_events;
+    for (int l = L_; l >= 1; --l) {
+        const LayerSpec& ls = cfg_.layers[l - 1];
+        const int ev_dz = emit_record(0);
+        int ev_dg = -1;
+        if (l > 1) {
+            const float* mask = cfg_.layers[l - 2].relu ? act_all_[l - 1] : nullptr;
+            GemmPlan g;
+            check(gemm_plan_dgrad(&g, Wl(l), ls.ld, dz_all_[l], act_ld_[l], dz_all_[l - 1], act_ld_[l - 1], rows, ls.in, ls.out,
+                                  mask, act_ld_[l - 1]));
+            add_gemm(g, 0, l);
+            ev_dg = emit_record(0);
+        }
+        const int w = sw(l);
+        use(w);
+        emit_wait(w, ev_dz);
+        if (fuse && ev_dg >= 0) emit_wait(w, ev_dg);      // W_l is updated in place: its last reader must be done
+        GemmPlan g;
+        check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
+                              Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0));
+        add_gemm(g, w, l);
+        if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
+            const int ev_g = emit_record(w);
+            use(s_dp_);
+            emit_wait(s_dp_, ev_g);
+            Op ar;
+            ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
+            ops_.push_back(ar);
+        }
+    }
+    if (!fuse) {
+        const int ev_main = emit_record(0);
+        use(s_dp_);
+        emit_wait(s_dp_, ev_main);
+        for (int w = 0; w < n_w_streams_; ++w) {
+            const int ws = 1 + n_mu_streams_ + w;
+            if (started[ws]) { const int e = emit_record(ws); emit_wait(s_dp_, e); }
+        }
+        Op sg;
+        sg.kind = OP_SGD; sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
+        ops_.push_back(sg);
+    }
+    for (size_t s = 1; s < streams_.size(); ++s)
+        if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
+    Op cp;
+    cp.kind = OP_MEMCPY_LOSS; cp.stream = 0;
+    ops_.push_back(cp);
+}
+
+void PipeEngine::finish_build() {
     kernels_per_step_ = 0;
     for (auto& op : ops_) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
@@ -374,10 +474,11 @@ void PipeEngine::exec(const Op& op) {
         case OP_GEMM: CUDA_CHECK(gemm_launch(gemms_[op.gemm], st)); break;
         case OP_LOSS_HEAD:
             CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, loss_dev_ + op.mu, op.rows,
-                                        op.cols, op.scalar, st));
+                                        op.cols, op.scalar, st, (int)op.n));
             break;
         case OP_SOFTMAX:
-            CUDA_CHECK(launch_loss_head(op.a, op.lda, nullptr, 0, op.b, op.ldb, nullptr, 0, nullptr, op.rows, op.cols, 0.f, st));
+            CUDA_CHECK(launch_loss_head(op.a, op.lda, nullptr, 0, op.b, op.ldb, nullptr, 0, nullptr, op.rows, op.cols, 0.f, st,
+                                        (int)op.n));
             break;
         case OP_ARGMAX:
             CUDA_CHECK(launch_argmax_correct(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, correct_dev_, st));

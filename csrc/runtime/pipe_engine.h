@@ -109,12 +109,15 @@ public:
     int y_ld() const { return y_ld_; }
     int64_t kernels_per_step() const { return kernels_per_step_; }
     int64_t graph_nodes() const { return graph_nodes_; }
+    bool coalesced() const { return coalesced_; }
     cudaStream_t main_stream() { return streams_[0]; }
     const EngineConfig& config() const { return cfg_; }
     std::string describe() const;
 
 private:
     void alloc_buffers();
+    void build_coalesced();
+    void finish_build();
     int new_event();
     void emit_wait(int stream, int ev);
     int emit_record(int stream);
@@ -128,6 +131,9 @@ private:
     std::vector<int> act_ld_;                    // per layer boundary 0..L
     std::vector<std::vector<float*>> act_, dz_;  // [mu][l]
     std::vector<float*> probs_;
+    std::vector<float*> act_all_, dz_all_;       // [l] contiguous over micro-batches
+    float* probs_all_ = nullptr;
+    bool coalesced_ = false;
     float *x_stage_ = nullptr, *y_stage_ = nullptr, *loss_dev_ = nullptr, *loss_host_ = nullptr;
     int* correct_dev_ = nullptr;
     int y_ld_ = 0;

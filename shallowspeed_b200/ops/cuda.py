@@ -30,7 +30,8 @@ def tma_ready(t: torch.Tensor) -> bool:
 
 def empty_padded(rows: int, cols: int, device) -> torch.Tensor:
     """[rows, cols] view of a [rows, round_up(cols, 4)] buffer (TMA-legal row pitch)."""
-    return torch.empty(rows, _round_up(cols, 4), dtype=torch.float32, device=device)[:, :cols]
+    # zeros: padding columns may be read by 16-byte-granular TMA accesses and must stay finite
+    return torch.zeros(rows, _round_up(cols, 4), dtype=torch.float32, device=device)[:, :cols]
 
 
 def as_tma(t: torch.Tensor) -> torch.Tensor:

@@ -49,10 +49,34 @@ def test_engine_matches_cpu_training(sched, use_graph):
     (mc, lc, _), (mg, lg, wg) = out["cpu"], out["cuda"]
     for a, b in zip(lc, lg):
         assert abs(a - b) < 2e-3 * max(1.0, abs(a))
-    for pc, pg in zip(mc.parameters(), mg.parameters()):
-        assert _frob(pg.data.cpu(), pc.data) < 2e-3          # weights after 3 SGD steps (TF32 math)
-    n_gemm = 4 * (7 + 6 + 7)                                  # fwd + dgrad (layer 1 skipped) + wgrad per micro-batch
-    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == n_gemm + 4   # + 4 loss heads; SGD fused
+    from shallowspeed_b200.layers import MLP
+
+    init = MLP(SIZES, 0, 1, 128)
+    for p0, pc, pg in zip(init.parameters(), mc.parameters(), mg.parameters()):
+        # compare the UPDATE (3 SGD steps): TF32 products => a few % in norm on the gradients
+        assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < 5e-2
+        assert _frob(pg.data.cpu(), pc.data) < 5e-2
+    # pp == 1: micro-batches are horizontally fused -> 7 fwd + 6 dgrad (layer 1 skipped) + 7 wgrad
+    # (SGD fused into the wgrad epilogue) + 1 loss head (one CTA per micro-batch)
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 21
+
+
+@pytest.mark.parametrize("sched", ["naive", "pipedream"])
+def test_engine_per_microbatch_path_matches_cpu(sched, monkeypatch):
+    """Same check with horizontal fusion disabled: every micro-batch is its own chain of
+    launches on its own stream (the path pipeline stages with p2p comm use)."""
+    from shallowspeed_b200.layers import MLP
+    from shallowspeed_b200.pipe import SCHEDULE_NAME_TO_CLS
+
+    monkeypatch.setenv("SSB_NO_COALESCE", "1")
+    out = _setup(SCHEDULE_NAME_TO_CLS[sched])
+    (mc, lc, _), (mg, lg, wg) = out["cpu"], out["cuda"]
+    for a, b in zip(lc, lg):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a))
+    init = MLP(SIZES, 0, 1, 128)
+    for p0, pc, pg in zip(init.parameters(), mc.parameters(), mg.parameters()):
+        assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < 5e-2
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 4 * (7 + 6 + 7) + 4 + 1
 
 
 def test_engine_is_bit_deterministic():
