@@ -67,6 +67,46 @@ cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 cudaError_t gemm_configure();   // opt every instantiation into > 48 KB dynamic smem (call outside graph capture)
 int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)
 
+// ---- fused data-parallel path (csrc/kernels/fused_dp.cu) ---------------------------------
+static constexpr int kMaxDp = 8;
+struct DpPeers {                 // symmetric-memory pointer tables (index = DP rank)
+    float* W[kMaxDp];            // weight arenas (owners publish updated tiles into every replica)
+    float* stage[kMaxDp];        // partial-gradient staging: [src][layer slots]
+    uint32_t* arrive[kMaxDp];    // arrive[owner][src * slots_per_src + slot] = epoch when src's partial landed
+    uint32_t* done[kMaxDp];      // done[rank][tile] = epoch when the tile's new weights landed on rank
+};
+struct DpLayerParams {
+    int m_total, n_total, k_total;   // out, in, micro-batch rows
+    int block_n, stages;
+    int n_tiles_m, n_tiles_n;
+    int dp, rank;
+    int64_t w_offset;                // float offset of the layer's [out, ld] block in the arena
+    int ldw;
+    int64_t stage_offset;            // float offset of the layer's slots inside one src region
+    int64_t stage_src_stride;        // floats per src region
+    int tile_flag_base, slot_flag_base, slots_per_src;
+    float lr;
+    const uint32_t* epoch_ptr;       // device step counter (bumped once per step, same value on all ranks)
+    const float* G;                  // dp_reduce_sgd: accumulated gradient block to reduce
+    int ldg;
+};
+struct FusedDpPlan {
+    CUtensorMap tmA, tmB;
+    DpLayerParams p;
+    DpPeers peers;
+    int grid;
+    int smem_bytes;
+};
+void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, int* n_tiles_n, int64_t* slots,
+                       int64_t* slot_floats);
+// dZ == nullptr: plan for dp_reduce_sgd (no GEMM)
+const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const float* X, int ldx, int rows,
+                          const DpLayerParams& lp, const DpPeers& peers, int max_ctas);
+cudaError_t fused_dp_configure();
+cudaError_t launch_fused_wgrad_dp(const FusedDpPlan& plan, cudaStream_t stream);
+cudaError_t launch_dp_reduce_sgd(const FusedDpPlan& plan, cudaStream_t stream);
+cudaError_t launch_bump_epoch(uint32_t* epoch, cudaStream_t stream);
+
 // ---- small fused kernels --------------------------------------------------------------
 // logits[rows, cols] (ld) -> probs (nullable) ; training: dlogits (softmax-Jacobian x MSE
 // grad, 1/batch_size inside) and loss_out[0] = sum((t-p)^2)/batch_size.

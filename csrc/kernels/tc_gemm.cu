@@ -298,6 +298,11 @@ static const char* make_tmap(CUtensorMap* map, const float* base, int inner, int
     return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
 }
 
+// MN-major operand map ([rows(K) x 32 mn] panels) for other translation units (fused_dp.cu)
+const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int outer, int ld) {
+    return make_tmap(map, base, inner, outer, ld, 32, true);
+}
+
 static int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 
 static void finish_plan(GemmPlan* plan) {

@@ -65,6 +65,25 @@ static torch::Tensor view_of(float* ptr, int64_t rows, int64_t cols, int64_t ld)
     return torch::from_blob(ptr, {rows, cols}, {ld, 1}, [](void*) {}, opts);
 }
 
+class PyDpContext {
+public:
+    PyDpContext(int dp, int rank, int64_t arena_numel, const std::vector<std::tuple<int, int, int64_t, int>>& layers, double lr)
+        : ctx_(std::make_unique<DpContext>(dp, rank, arena_numel, layers, (float)lr)) {}
+    py::bytes export_handles() { return py::bytes(ctx_->export_handles()); }
+    void open_peers(const std::vector<std::string>& handles) { ctx_->open_peers(handles); }
+    torch::Tensor weights() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA, dev);
+        return torch::from_blob(ctx_->weights(), {ctx_->arena_numel()}, [](void*) {}, opts);
+    }
+    int64_t stage_bytes() { return ctx_->stage_bytes(); }
+    DpContext* get() { return ctx_.get(); }
+
+private:
+    std::unique_ptr<DpContext> ctx_;
+};
+
 class PyEngine {
 public:
     PyEngine(const std::vector<std::tuple<int, int, int, int64_t, int>>& layers, py::dict cfg, torch::Tensor weights,
@@ -87,6 +106,7 @@ public:
     }
     void set_pp_comm(std::shared_ptr<NcclComm> c) { pp_ = c; engine_->set_pp_comm(c->get()); }
     void set_dp_comm(std::shared_ptr<NcclComm> c) { dp_ = c; engine_->set_dp_comm(c->get()); }
+    void set_dp_context(std::shared_ptr<PyDpContext> c) { dpctx_ = c; engine_->set_dp_context(c->get()); }
     void build(const std::vector<std::tuple<int, int, int>>& instrs) {
         c10::cuda::CUDAGuard guard(weights_.device());
         engine_->build(instrs);
@@ -133,6 +153,7 @@ public:
 private:
     torch::Tensor weights_, grads_;
     std::shared_ptr<NcclComm> pp_, dp_;
+    std::shared_ptr<PyDpContext> dpctx_;
     std::unique_ptr<PipeEngine> engine_;
 };
 
@@ -143,10 +164,17 @@ void bind_runtime(py::module_& m) {
         .def("warmup", &NcclComm::warmup)
         .def("nranks", &NcclComm::nranks)
         .def("rank", &NcclComm::rank);
+    py::class_<PyDpContext, std::shared_ptr<PyDpContext>>(m, "DpContext")
+        .def(py::init<int, int, int64_t, const std::vector<std::tuple<int, int, int64_t, int>>&, double>())
+        .def("export_handles", &PyDpContext::export_handles)
+        .def("open_peers", &PyDpContext::open_peers)
+        .def("weights", &PyDpContext::weights)
+        .def("stage_bytes", &PyDpContext::stage_bytes);
     py::class_<PyEngine>(m, "PipeEngine")
         .def(py::init<const std::vector<std::tuple<int, int, int, int64_t, int>>&, py::dict, torch::Tensor, torch::Tensor>())
         .def("set_pp_comm", &PyEngine::set_pp_comm)
         .def("set_dp_comm", &PyEngine::set_dp_comm)
+        .def("set_dp_context", &PyEngine::set_dp_context)
         .def("build", &PyEngine::build)
         .def("stage_inputs", &PyEngine::stage_inputs)
         .def("run", &PyEngine::run)

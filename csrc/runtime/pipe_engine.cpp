@@ -29,6 +29,8 @@ enum : int {
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// leave some SMs to the concurrently running dgrad chain; also bounds co-residency needs
+static constexpr int kFusedDpMaxCtas = 120;
 
 PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, int64_t arena_numel)
     : cfg_(cfg), W_(weights), G_(grads), arena_numel_(arena_numel), L_((int)cfg.layers.size()) {
@@ -177,6 +179,13 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
     std::vector<bool> first_write(L_ + 1, true);
     std::vector<bool> sw_joined(streams_.size(), false);
     std::vector<int> ev_allreduce;
+    std::vector<std::pair<int, int>> pending_dp;         // (layer, event after its final wgrad)
+    if (cfg_.dp_mode == 2 && cfg_.training) {
+        Op be;
+        be.kind = OP_BUMP_EPOCH; be.stream = 0;
+        ops_.insert(ops_.begin(), be);   // before the 'begin' event every stream forks from
+        ++kernels_extra_;
+    }
     auto add_gemm = [&](const GemmPlan& g, int stream, int layer, int mu) {
         gemms_.push_back(g);
         Op op;
@@ -299,6 +308,7 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
                         ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
                         ops_.push_back(ar);
                     }
+                    if (final_bwd && cfg_.dp_mode == 2) pending_dp.push_back({l, emit_record(w)});
                     if (l > 1 || !first) {
                         const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
                         GemmPlan g2;
@@ -308,9 +318,31 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
                     }
                 }
                 ev_bwd[mu] = emit_record(s);
+                if (final_bwd && cfg_.dp_mode == 2) {
+                    // G is final: reduce across replicas + SGD + weight broadcast in ONE kernel per layer
+                    // over peer memory.  W is rewritten, so every reader (all micro-batches) must be done.
+                    if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
+                    use(s_dp_);
+                    for (int m2 = 0; m2 < M; ++m2)
+                        if (ev_bwd[m2] >= 0) emit_wait(s_dp_, ev_bwd[m2]);
+                        else if (ev_fwd[m2] >= 0) emit_wait(s_dp_, ev_fwd[m2]);
+                    for (auto& pd : pending_dp) {
+                        emit_wait(s_dp_, pd.second);
+                        DpLayerParams lp = dp_ctx_->layer_params(pd.first - 1);
+                        lp.G = Gl(pd.first);
+                        FusedDpPlan fp;
+                        check(fused_dp_plan(&fp, nullptr, 0, nullptr, 0, mb, lp, dp_ctx_->peers(), kFusedDpMaxCtas));
+                        dp_plans_.push_back(fp);
+                        Op fo;
+                        fo.kind = OP_DP_REDUCE; fo.stream = s_dp_; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = pd.first;
+                        ops_.push_back(fo);
+                    }
+                    pending_dp.clear();
+                }
                 break;
             }
             case I_OPT_STEP: {
+                if (cfg_.dp_mode == 2) break;            // the update already happened inside the fused kernels
                 {
                     use(s_dp_);
                     for (int m2 = 0; m2 < M; ++m2)
@@ -394,7 +426,14 @@ void PipeEngine::build_coalesced() {
     ops_.push_back(lh);
 
     const bool fuse = (cfg_.dp_mode == 0);
-    std::vector<int> tail_events;
+    const bool fused_dp = (cfg_.dp_mode == 2);
+    if (fused_dp) {
+        if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
+        Op be;
+        be.kind = OP_BUMP_EPOCH; be.stream = 0;
+        ops_.insert(ops_.begin(), be);   // before the 'begin' event every stream forks from               // first thing of the step, before any fork
+        ++kernels_extra_;
+    }
     for (int l = L_; l >= 1; --l) {
         const LayerSpec& ls = cfg_.layers[l - 1];
         const int ev_dz = emit_record(0);
@@ -406,6 +445,21 @@ void PipeEngine::build_coalesced() {
                                   mask, act_ld_[l - 1]));
             add_gemm(g, 0, l);
             ev_dg = emit_record(0);
+        }
+        if (fused_dp) {
+            // ONE kernel per layer: wgrad GEMM -> NVLink push -> owner reduce -> SGD -> weight broadcast.
+            // All fused kernels of all layers go through ONE stream in the same order on every rank.
+            use(s_dp_);
+            emit_wait(s_dp_, ev_dz);
+            if (ev_dg >= 0) emit_wait(s_dp_, ev_dg);
+            FusedDpPlan fp;
+            check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, dp_ctx_->layer_params(l - 1),
+                                dp_ctx_->peers(), kFusedDpMaxCtas));
+            dp_plans_.push_back(fp);
+            Op fo;
+            fo.kind = OP_FUSED_DP; fo.stream = s_dp_; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = l;
+            ops_.push_back(fo);
+            continue;
         }
         const int w = sw(l);
         use(w);
@@ -424,7 +478,7 @@ void PipeEngine::build_coalesced() {
             ops_.push_back(ar);
         }
     }
-    if (!fuse) {
+    if (!fuse && !fused_dp) {
         const int ev_main = emit_record(0);
         use(s_dp_);
         emit_wait(s_dp_, ev_main);
@@ -447,7 +501,8 @@ void PipeEngine::finish_build() {
     kernels_per_step_ = 0;
     for (auto& op : ops_) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
-            op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP)
+            op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
+            op.kind == OP_BUMP_EPOCH)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -455,6 +510,7 @@ void PipeEngine::finish_build() {
     // kernel attributes are configured up front (never inside a capture); communicators are
     // warmed up by their creator.  No eager pass here: a training step mutates the weights.
     CUDA_CHECK(gemm_configure());
+    if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
     if (cfg_.use_graph) {
         CUDA_CHECK(cudaStreamBeginCapture(streams_[0], cudaStreamCaptureModeThreadLocal));
         walk(true);
@@ -499,6 +555,9 @@ void PipeEngine::exec(const Op& op) {
             NCCL_CHECK(ncclGroupEnd());
             break;
         }
+        case OP_FUSED_DP: CUDA_CHECK(launch_fused_wgrad_dp(dp_plans_[op.gemm], st)); break;
+        case OP_DP_REDUCE: CUDA_CHECK(launch_dp_reduce_sgd(dp_plans_[op.gemm], st)); break;
+        case OP_BUMP_EPOCH: CUDA_CHECK(launch_bump_epoch(dp_ctx_->epoch_ptr(), st)); break;
         case OP_MEMCPY_LOSS:
             CUDA_CHECK(cudaMemcpyAsync(loss_host_, loss_dev_, sizeof(float) * cfg_.n_mu, cudaMemcpyDeviceToHost, st));
             break;

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "kernels/kernels.h"
+#include "runtime/dp_context.h"
 
 struct ncclComm;
 typedef struct ncclComm* ncclComm_t;
@@ -39,7 +40,7 @@ struct LayerSpec {
 
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
-    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX
+    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -86,6 +87,7 @@ public:
     // communicators (optional): created by the caller from ncclUniqueIds exchanged over torch.distributed
     void set_pp_comm(ncclComm_t comm) { pp_comm_ = comm; }
     void set_dp_comm(ncclComm_t comm) { dp_comm_ = comm; }
+    void set_dp_context(DpContext* ctx) { dp_ctx_ = ctx; }   // fused in-kernel DP reduction (dp_mode 2)
 
     // instrs: (opcode, buffer_id, mubatch_id) triples from parallel.instructions.encode
     void build(const std::vector<std::tuple<int, int, int>>& instrs);
@@ -142,10 +144,13 @@ private:
     std::vector<cudaStream_t> streams_;
     std::vector<cudaEvent_t> events_;
     std::vector<GemmPlan> gemms_;
+    std::vector<FusedDpPlan> dp_plans_;
+    DpContext* dp_ctx_ = nullptr;
     std::vector<Op> ops_;
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t graph_exec_ = nullptr;
     int64_t kernels_per_step_ = 0, graph_nodes_ = 0;
+    int kernels_extra_ = 0;
     ncclComm_t pp_comm_ = nullptr, dp_comm_ = nullptr;
     int n_mu_streams_ = 1, n_w_streams_ = 1;
     int s_comm_ = 0, s_dp_ = 0;

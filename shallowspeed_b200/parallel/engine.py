@@ -27,6 +27,25 @@ def _C():
     return mod
 
 
+def make_dp_context(comm: Comm, model, lr: float):
+    """Symmetric memory for the fused DP kernels: allocate, exchange CUDA IPC handles over
+    torch.distributed, map the peers, and move the model's weight arena into it."""
+    assert isinstance(comm, TorchComm)
+    import torch.distributed as dist
+
+    arena = model.arena
+    layers = [(lin.in_dims, lin.out_dims, int(arena.offsets[lin.block_index]), int(arena.lds[lin.block_index]))
+              for lin in model.linears]
+    ctx = _C().DpContext(comm.size, comm.rank, int(arena.weights.numel()), layers, float(lr))
+    blobs = [None] * comm.size
+    dist.all_gather_object(blobs, bytes(ctx.export_handles()), group=comm.group)
+    ctx.open_peers(blobs)
+    arena.rebind(ctx.weights(), arena.grads, copy=True)      # weights now live in symmetric memory
+    torch.cuda.synchronize()
+    dist.barrier(group=comm.group)
+    return ctx
+
+
 def make_nccl_comm(comm: Comm):
     """Create a native ncclComm for the ranks of a ``TorchComm`` (unique id travels over
     torch.distributed).  Returns None for size-1 communicators."""
@@ -60,14 +79,20 @@ class NativeWorker:
         else:
             self.dp_mode = comm_mode
         # native communicators are shared between the train and the validation worker
+        self.lr = optimizer.lr if optimizer is not None else 0.0
+        self._dp_ctx = None
         if share is not None:
             self._pp_nccl, self._dp_nccl = share._pp_nccl, share._dp_nccl
         else:
             self._pp_nccl = make_nccl_comm(self.pp_comm)
-            self._dp_nccl = make_nccl_comm(self.dp_comm) if dp_comm is not None else None
+            self._dp_nccl = None
+            if dp_comm is not None and self.dp_comm.Get_size() > 1:
+                if self.dp_mode == "fused":
+                    self._dp_ctx = make_dp_context(self.dp_comm, model, self.lr)
+                else:
+                    self._dp_nccl = make_nccl_comm(self.dp_comm)
         self._engines = {}
         self._last_engine = None
-        self.lr = optimizer.lr if optimizer is not None else 0.0
 
     # ------------------------------------------------------------------ plan cache
     def _key(self, sched: Schedule):
@@ -93,6 +118,8 @@ class NativeWorker:
             eng.set_pp_comm(self._pp_nccl)
         if self._dp_nccl is not None and training:
             eng.set_dp_comm(self._dp_nccl)
+        if self._dp_ctx is not None and training:
+            eng.set_dp_context(self._dp_ctx)
         torch.cuda.synchronize(self.device)
         eng.build([encode(i) for i in flatten(list(sched.steps()))])
         return eng
