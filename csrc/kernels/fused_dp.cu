@@ -46,12 +46,15 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord tile_coord(const DpLayerParams& p, int t) {
     TileCoord c;
-    c.t = t; c.mt = t / p.n_tiles_n; c.nt = t % p.n_tiles_n; c.owner = t % p.dp; c.slot = t / p.dp;
+    c.t = t; c.mt = t / p.n_tiles_n; c.nt = t % p.n_tiles_n; c.owner = t % p.dp;
+    c.slot = p.one_shot ? t : t / p.dp;
     return c;
 }
 __device__ __forceinline__ int64_t slot_floats(const DpLayerParams& p) { return (int64_t)kBlockM * p.block_n + kBlockM; }
-__device__ __forceinline__ float* stage_slot(const DpPeers& peers, const DpLayerParams& p, int owner, int src, int slot) {
-    return peers.stage[owner] + (int64_t)src * p.stage_src_stride + p.stage_offset + (int64_t)slot * slot_floats(p);
+__device__ __forceinline__ float* stage_slot(const DpPeers& peers, const DpLayerParams& p, int owner, int src, int slot,
+                                             uint32_t epoch) {
+    return peers.stage[owner] + (int64_t)src * p.stage_src_stride + p.stage_offset + (int64_t)slot * slot_floats(p) +
+           (p.one_shot ? (int64_t)(epoch & 1u) * p.stage_parity_stride : 0);
 }
 
 // ---- phase B: the owner reduces one tile in rank order, applies SGD, publishes the weights
@@ -66,7 +69,8 @@ __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& 
     const int m0 = tc.mt * (int)kBlockM, n0 = tc.nt * p.block_n;
     const int f4_per_row = p.block_n / 4;
     const int total_f4 = (int)kBlockM * f4_per_row;
-    const float* st0 = stage_slot(peers, p, me, 0, tc.slot);
+    const float* st0 = stage_slot(peers, p, me, 0, tc.slot, epoch);
+    const int n_pub = p.one_shot ? 1 : p.dp;              // one-shot: every replica updates only its own W
     const bool vec_ok = (p.ldw % 4) == 0;
     for (int f = tid; f < total_f4; f += nthreads) {
         const int r = f / f4_per_row, c4 = f % f4_per_row;
@@ -81,12 +85,14 @@ __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& 
         if (vec_ok && n + 3 < p.n_total) {
             float4 w = *reinterpret_cast<const float4*>(peers.W[me] + woff);
             w.x -= p.lr * sum.x; w.y -= p.lr * sum.y; w.z -= p.lr * sum.z; w.w -= p.lr * sum.w;
-            for (int r2 = 0; r2 < p.dp; ++r2) *reinterpret_cast<float4*>(peers.W[r2] + woff) = w;   // publish to all replicas
+            if (n_pub == 1) *reinterpret_cast<float4*>(peers.W[me] + woff) = w;
+            else for (int r2 = 0; r2 < p.dp; ++r2) *reinterpret_cast<float4*>(peers.W[r2] + woff) = w;   // publish to all replicas
         } else {
             const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
             for (int e = 0; e < 4 && n + e < p.n_total; ++e) {
                 const float w = peers.W[me][woff + e] - p.lr * sv[e];
-                for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][woff + e] = w;
+                if (n_pub == 1) peers.W[me][woff + e] = w;
+                else for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][woff + e] = w;
             }
         }
     }
@@ -99,12 +105,16 @@ __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& 
                 sum += ld_cg_f(st0 + (int64_t)s * p.stage_src_stride + (int64_t)kBlockM * p.block_n + r);
             const int64_t boff = p.w_offset + (int64_t)m * p.ldw + p.n_total;
             const float b = peers.W[me][boff] - p.lr * sum;
-            for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][boff] = b;
+            if (n_pub == 1) peers.W[me][boff] = b;
+            else for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][boff] = b;
         }
     }
-    __threadfence_system();
+    if (p.one_shot) return;                               // nothing to publish, nobody waits
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    if (tid < p.dp) st_release_sys(peers.done[tid] + p.tile_flag_base + tc.t, epoch);
+    if (tid == 0) {
+        __threadfence_system();                            // one cumulative fence after the CTA barrier
+        for (int r2 = 0; r2 < p.dp; ++r2) st_release_sys(peers.done[r2] + p.tile_flag_base + tc.t, epoch);
+    }
 }
 
 __device__ __forceinline__ void dp_wait_tile_done(const DpPeers& peers, const DpLayerParams& p, const TileCoord& tc, uint32_t epoch) {
@@ -231,31 +241,42 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             mbar_wait(tmem_full_bar, tile_i & 1);
             tc_fence_after();
-            float* dst = stage_slot(peers, p, tc.owner, p.rank, tc.slot);
-            float* drow = dst + (int64_t)m_local * p.block_n;
+            const int n_dst = p.one_shot ? p.dp : 1;
             for (int c = 0; c < p.block_n; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + c, v);
+                for (int d = 0; d < n_dst; ++d) {                 // two-shot: the owner only; one-shot: every replica
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    float* drow = stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch) + (int64_t)m_local * p.block_n;
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4)
-                    *reinterpret_cast<float4*>(drow + c + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                    for (int g4 = 0; g4 < 4; ++g4)
+                        *reinterpret_cast<float4*>(drow + c + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                }
             }
-            if (tc.nt == 0) dst[(int64_t)kBlockM * p.block_n + m_local] = dbsum;
+            if (tc.nt == 0)
+                for (int d = 0; d < n_dst; ++d) {
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch)[(int64_t)kBlockM * p.block_n + m_local] = dbsum;
+                }
             tc_fence_before();
-            __threadfence_system();                               // partial visible system-wide before the flag
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar);           // MMA of the next tile may overwrite TMEM
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (etid == 0)
-                st_release_sys(peers.arrive[tc.owner] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+            if (etid == 0) {
+                __threadfence_system();                           // partial visible system-wide before the flag(s)
+                for (int d = 0; d < n_dst; ++d) {
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    st_release_sys(peers.arrive[dst_rank] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+                }
+            }
         }
         // ---------------- phase B: reduce + SGD + publish the tiles this replica owns
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const TileCoord tc = tile_coord(p, t);
-            if (tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1);
+            if (p.one_shot || tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1);
         }
         // ---------------- phase C: wait for the owners of my other tiles
-        if (etid == 0) {
+        if (etid == 0 && !p.one_shot) {
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const TileCoord tc = tile_coord(p, t);
                 if (tc.owner != p.rank) dp_wait_tile_done(peers, p, tc, epoch);
@@ -280,7 +301,7 @@ __global__ void __launch_bounds__(128, 1) dp_reduce_sgd_kernel(const DpLayerPara
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t);
         const int m0 = tc.mt * (int)kBlockM, n0 = tc.nt * p.block_n;
-        float* dst = stage_slot(peers, p, tc.owner, p.rank, tc.slot);
+        const int n_dst = p.one_shot ? p.dp : 1;
         for (int f = tid; f < (int)kBlockM * f4_per_row; f += blockDim.x) {
             const int r = f / f4_per_row, c4 = f % f4_per_row;
             const int m = m0 + r, n = n0 + 4 * c4;
@@ -295,21 +316,29 @@ __global__ void __launch_bounds__(128, 1) dp_reduce_sgd_kernel(const DpLayerPara
                     if (n + 3 < p.n_total) v.w = g[3];
                 }
             }
-            *reinterpret_cast<float4*>(dst + (int64_t)r * p.block_n + 4 * c4) = v;
+            for (int d = 0; d < n_dst; ++d) {
+                float* dst = stage_slot(peers, p, p.one_shot ? d : tc.owner, p.rank, tc.slot, epoch);
+                *reinterpret_cast<float4*>(dst + (int64_t)r * p.block_n + 4 * c4) = v;
+            }
         }
         if (tc.nt == 0)
-            for (int r = tid; r < (int)kBlockM; r += blockDim.x)
-                dst[(int64_t)kBlockM * p.block_n + r] = (m0 + r < p.m_total) ? p.G[(int64_t)(m0 + r) * p.ldg + p.n_total] : 0.f;
-        __threadfence_system();
+            for (int r = tid; r < (int)kBlockM; r += blockDim.x) {
+                const float v = (m0 + r < p.m_total) ? p.G[(int64_t)(m0 + r) * p.ldg + p.n_total] : 0.f;
+                for (int d = 0; d < n_dst; ++d)
+                    stage_slot(peers, p, p.one_shot ? d : tc.owner, p.rank, tc.slot, epoch)[(int64_t)kBlockM * p.block_n + r] = v;
+            }
         __syncthreads();
-        if (tid == 0)
-            st_release_sys(peers.arrive[tc.owner] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+        if (tid == 0) {
+            __threadfence_system();
+            for (int d = 0; d < n_dst; ++d)
+                st_release_sys(peers.arrive[p.one_shot ? d : tc.owner] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+        }
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(p, t);
-        if (tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, tid, 128, 1);
+        if (p.one_shot || tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, tid, 128, 1);
     }
-    if (tid == 0) {
+    if (tid == 0 && !p.one_shot) {
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const TileCoord tc = tile_coord(p, t);
             if (tc.owner != p.rank) dp_wait_tile_done(peers, p, tc, epoch);
@@ -322,12 +351,13 @@ __global__ void bump_epoch_kernel(uint32_t* epoch) { *epoch = *epoch + 1; }
 // =========================================================================== host side
 const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int outer, int ld);   // tc_gemm.cu
 
-void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, int* n_tiles_n, int64_t* slots, int64_t* slot_floats_out) {
+void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, int* n_tiles_n, int64_t* slots, int64_t* slot_floats_out,
+                       int one_shot) {
     *block_n = in >= 128 ? 128 : (in + 31) / 32 * 32;
     *n_tiles_m = (out + (int)kBlockM - 1) / (int)kBlockM;
     *n_tiles_n = (in + *block_n - 1) / *block_n;
     const int64_t tiles = (int64_t)*n_tiles_m * *n_tiles_n;
-    *slots = (tiles + dp - 1) / dp;
+    *slots = one_shot ? tiles : (tiles + dp - 1) / dp;
     *slot_floats_out = (int64_t)kBlockM * *block_n + kBlockM;
 }
 

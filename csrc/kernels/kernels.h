@@ -89,6 +89,11 @@ struct DpLayerParams {
     const uint32_t* epoch_ptr;       // device step counter (bumped once per step, same value on all ranks)
     const float* G;                  // dp_reduce_sgd: accumulated gradient block to reduce
     int ldg;
+    // one_shot: small (latency-bound) layers - every replica pushes its partial tile to ALL replicas
+    // and every replica reduces every tile itself in the same fixed rank order (bit-identical results,
+    // one NVLink hop instead of two).  Staging is double-buffered by epoch parity (stage_parity_stride).
+    int one_shot;
+    int64_t stage_parity_stride;
 };
 struct FusedDpPlan {
     CUtensorMap tmA, tmB;
@@ -98,7 +103,7 @@ struct FusedDpPlan {
     int smem_bytes;
 };
 void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, int* n_tiles_n, int64_t* slots,
-                       int64_t* slot_floats);
+                       int64_t* slot_floats, int one_shot);
 // dZ == nullptr: plan for dp_reduce_sgd (no GEMM)
 const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const float* X, int ldx, int rows,
                           const DpLayerParams& lp, const DpPeers& peers, int max_ctas);

@@ -1,5 +1,7 @@
 #include "runtime/dp_context.h"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -23,7 +25,11 @@ DpContext::DpContext(int dp, int rank, int64_t arena_numel, const std::vector<st
     for (auto& t : layers) {
         DpLayerGeom g{};
         g.in = std::get<0>(t); g.out = std::get<1>(t); g.w_offset = std::get<2>(t); g.ld = std::get<3>(t);
-        dp_layer_geometry(g.in, g.out, dp, &g.block_n, &g.n_tiles_m, &g.n_tiles_n, &g.slots, &g.slot_floats);
+        // latency-bound layers (<= 2 MB of gradient) use the one-shot protocol, big ones two-shot
+        g.one_shot = ((int64_t)g.in * g.out * 4 <= (2 << 20)) && !getenv("SSB_DP_TWO_SHOT");
+        if (getenv("SSB_DP_ONE_SHOT")) g.one_shot = 1;
+        dp_layer_geometry(g.in, g.out, dp, &g.block_n, &g.n_tiles_m, &g.n_tiles_n, &g.slots, &g.slot_floats, g.one_shot);
+        total_ctas_ += g.n_tiles_m * g.n_tiles_n;
         g.stage_offset = stage_off;
         g.slot_flag_base = slot_base;
         g.tile_flag_base = tile_base;
@@ -32,7 +38,8 @@ DpContext::DpContext(int dp, int rank, int64_t arena_numel, const std::vector<st
         tile_base += g.n_tiles_m * g.n_tiles_n;
         geom_.push_back(g);
     }
-    stage_src_stride_ = round_up64(std::max<int64_t>(stage_off, 64), 64);
+    stage_parity_stride_ = round_up64(std::max<int64_t>(stage_off, 64), 64);
+    stage_src_stride_ = 2 * stage_parity_stride_;        // x2: one-shot slots are double-buffered by epoch parity
     slots_per_src_ = std::max(slot_base, 1);
     tiles_total_ = std::max(tile_base, 1);
     auto alloc = [](void** p, size_t bytes) {
@@ -94,6 +101,8 @@ DpLayerParams DpContext::layer_params(int i) const {
     p.lr = lr_;
     p.epoch_ptr = epoch_;
     p.G = nullptr; p.ldg = g.ld;
+    p.one_shot = g.one_shot;
+    p.stage_parity_stride = stage_parity_stride_;
     return p;
 }
 

@@ -24,6 +24,7 @@ struct DpLayerGeom {
     int block_n, n_tiles_m, n_tiles_n;
     int64_t slots, slot_floats, stage_offset;
     int tile_flag_base, slot_flag_base;
+    int one_shot;
 };
 
 class DpContext {
@@ -44,13 +45,15 @@ public:
     int rank() const { return rank_; }
     int64_t stage_bytes() const { return (int64_t)dp_ * stage_src_stride_ * 4; }
     const std::vector<DpLayerGeom>& geometry() const { return geom_; }
+    int total_ctas() const { return total_ctas_; }   // sum of tiles over layers: all co-resident if <= #SMs
 
 private:
     int dp_, rank_;
     int64_t arena_numel_;
     float lr_;
     std::vector<DpLayerGeom> geom_;
-    int64_t stage_src_stride_ = 0;
+    int64_t stage_src_stride_ = 0, stage_parity_stride_ = 0;
+    int total_ctas_ = 0;
     int slots_per_src_ = 0, tiles_total_ = 0;
     float *W_ = nullptr, *stage_ = nullptr;
     uint32_t *arrive_ = nullptr, *done_ = nullptr, *epoch_ = nullptr;

@@ -449,15 +449,17 @@ void PipeEngine::build_coalesced() {
         if (fused_dp) {
             // ONE kernel per layer: wgrad GEMM -> NVLink push -> owner reduce -> SGD -> weight broadcast.
             // All fused kernels of all layers go through ONE stream in the same order on every rank.
-            use(s_dp_);
-            emit_wait(s_dp_, ev_dz);
-            if (ev_dg >= 0) emit_wait(s_dp_, ev_dg);
+            // (big layers).  When the CTAs of ALL layers fit on the chip together they may overlap freely.
+            const int sdp = (dp_ctx_->total_ctas() <= kFusedDpMaxCtas) ? sw(l) : s_dp_;
+            use(sdp);
+            emit_wait(sdp, ev_dz);
+            if (ev_dg >= 0) emit_wait(sdp, ev_dg);
             FusedDpPlan fp;
             check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, dp_ctx_->layer_params(l - 1),
                                 dp_ctx_->peers(), kFusedDpMaxCtas));
             dp_plans_.push_back(fp);
             Op fo;
-            fo.kind = OP_FUSED_DP; fo.stream = s_dp_; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = l;
+            fo.kind = OP_FUSED_DP; fo.stream = sdp; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = l;
             ops_.push_back(fo);
             continue;
         }

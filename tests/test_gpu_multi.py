@@ -12,11 +12,13 @@ SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
 GBS, N_MU, LR, STEPS = 128, 4, 0.05, 4
 
 
-def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce):
+def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce, two_shot=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     if not coalesce:
         os.environ["SSB_NO_COALESCE"] = "1"
+    if two_shot:
+        os.environ["SSB_DP_TWO_SHOT"] = "1"
     import torch.distributed as dist
 
     from shallowspeed_b200.dataset import Dataset, synthetic_mnist
@@ -69,14 +71,14 @@ def _cpu_oracle():
     return [p.data.clone() for p in model.parameters()], MLP(SIZES, 0, 1, GBS)
 
 
-def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True):
+def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True, two_shot=False):
     import torch.multiprocessing as mp
 
     world = dp * pp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29800 + (os.getpid() + dp * 7 + pp * 13 + len(sched)) % 150
-    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce, two_shot), nprocs=world, join=True)
     got = [p for s in range(pp) for p in torch.load(tmp_path / f"stage{s}.pt")["params"]]
     ref, init = _cpu_oracle()
     for p0, a, b in zip(init.parameters(), got, ref):
@@ -89,8 +91,14 @@ def test_dp2(comm_mode, tmp_path):
     _run(2, 1, "naive", comm_mode, tmp_path)
 
 
-def test_dp2_fused_per_microbatch_path(tmp_path):
-    _run(2, 1, "gpipe", "fused", tmp_path, coalesce=False)
+def test_dp2_fused_two_shot_protocol(tmp_path):
+    """owner-reduces / publishes-weights variant (used for big layers), forced on the small model"""
+    _run(2, 1, "naive", "fused", tmp_path, two_shot=True)
+
+
+@pytest.mark.parametrize("two_shot", [False, True])
+def test_dp2_fused_per_microbatch_path(two_shot, tmp_path):
+    _run(2, 1, "gpipe", "fused", tmp_path, coalesce=False, two_shot=two_shot)
 
 
 @pytest.mark.parametrize("sched", ["naive", "gpipe", "pipedream"])
