@@ -427,12 +427,15 @@ void PipeEngine::build_coalesced() {
 
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
+    int ev_bump = -1;
     if (fused_dp) {
         if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
+        // step counter for the flag protocol: bumped on the DP stream, off the forward critical path
+        use(s_dp_);
         Op be;
-        be.kind = OP_BUMP_EPOCH; be.stream = 0;
-        ops_.insert(ops_.begin(), be);   // before the 'begin' event every stream forks from               // first thing of the step, before any fork
-        ++kernels_extra_;
+        be.kind = OP_BUMP_EPOCH; be.stream = s_dp_;
+        ops_.push_back(be);
+        ev_bump = emit_record(s_dp_);
     }
     for (int l = L_; l >= 1; --l) {
         const LayerSpec& ls = cfg_.layers[l - 1];
@@ -452,6 +455,7 @@ void PipeEngine::build_coalesced() {
             // (big layers).  When the CTAs of ALL layers fit on the chip together they may overlap freely.
             const int sdp = (dp_ctx_->total_ctas() <= kFusedDpMaxCtas) ? sw(l) : s_dp_;
             use(sdp);
+            if (sdp != s_dp_) emit_wait(sdp, ev_bump);
             emit_wait(sdp, ev_dz);
             if (ev_dg >= 0) emit_wait(sdp, ev_dg);
             FusedDpPlan fp;
