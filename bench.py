@@ -167,7 +167,10 @@ def run_ours(args):
 
     def e2e_step(i):
         j = i % pool
-        losses.append(trainer.step(x_host[j], y_host[j]))      # H2D inputs + D2H loss every step
+        # public API: H2D of this step's inputs from pinned host memory + compute + D2H of its loss, every
+        # step; the host consumes the loss of the previous step (one-step-lagged readback) so copies,
+        # compute and read-back of neighbouring steps overlap
+        losses.append(trainer.step_pipelined(x_host[j], y_host[j]))
 
     for i in range(args.warmup):
         dev_step(i)
@@ -176,6 +179,7 @@ def run_ours(args):
         for i in range(max(3, args.warmup // 4)):
             e2e_step(i)
         ms_e2e = timed(lambda i: e2e_step(args.warmup + i), args.steps)
+        losses.append(trainer.flush())
     ms_dev, ms_e2e = max_over_ranks(ms_dev, dev), max_over_ranks(ms_e2e, dev)
     clocks = clk.summary()
 

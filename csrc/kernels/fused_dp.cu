@@ -170,7 +170,7 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.epoch_ptr);
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // converged warp, elect.sync-chosen issuing lane
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int m0 = (t / p.n_tiles_n) * kBlockM, n0 = (t % p.n_tiles_n) * p.block_n;
@@ -178,19 +178,23 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-                    const uint32_t a_dst = smem_base + s * stage_bytes, b_dst = a_dst + kABytes;
-                    const int k0 = kb * kBlockK;
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                        const uint32_t a_dst = smem_base + s * stage_bytes, b_dst = a_dst + kABytes;
+                        const int k0 = kb * kBlockK;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) tma_load_2d(a_dst + i * kPanelBytes, &tmA, full_bar(s), m0 + 32 * i, k0);
-                    for (int j = 0; j < p.block_n / 32; ++j)
-                        tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
+                        for (int i = 0; i < 4; ++i) tma_load_2d(a_dst + i * kPanelBytes, &tmA, full_bar(s), m0 + 32 * i, k0);
+                        for (int j = 0; j < p.block_n / 32; ++j)
+                            tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma_idesc_tf32(kBlockM, p.block_n, 1u, 1u);
+            const uint32_t mn_hi = umma_desc_hi(512u, 1u);
             int it = 0, tile_i = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
                 mbar_wait(tmem_empty_bar, (tile_i & 1) ^ 1);      // epilogue drained the accumulator
@@ -201,15 +205,17 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t a_src = smem_base + s * stage_bytes, b_src = a_src + kABytes;
+                    const uint32_t a_lo = umma_desc_lo(a_src, kPanelBytes), b_lo = umma_desc_lo(b_src, kPanelBytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t adesc = umma_desc_mn_sw128_32b(a_src + k4 * 1024u, kPanelBytes, 512u);
-                        const uint64_t bdesc = umma_desc_mn_sw128_32b(b_src + k4 * 1024u, kPanelBytes, 512u);
-                        umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc,
+                                      (kb | k4) != 0 ? 1u : 0u);
+                        umma_commit(empty_bar(s));
+                        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
                     }
-                    umma_commit(empty_bar(s));
+                    __syncwarp();
                 }
-                umma_commit(tmem_full_bar);
             }
         }
     } else {

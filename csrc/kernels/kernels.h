@@ -2,6 +2,7 @@
 // .cu files compile stand-alone with nvcc and the C++ runtime can call them directly).
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -111,6 +112,44 @@ cudaError_t fused_dp_configure();
 cudaError_t launch_fused_wgrad_dp(const FusedDpPlan& plan, cudaStream_t stream);
 cudaError_t launch_dp_reduce_sgd(const FusedDpPlan& plan, cudaStream_t stream);
 cudaError_t launch_bump_epoch(uint32_t* epoch, cudaStream_t stream);
+
+// ---- layer-chain kernel (csrc/kernels/mlp_chain.cu) --------------------------------------
+static constexpr int kChainMaxLayers = 16;
+struct ChainLayer {
+    int in, out, relu, ldw;
+    int64_t w_off;                   // float offset of the [out, ld] block in the weight arena
+};
+struct ChainParams {
+    int n_layers;
+    ChainLayer layers[kChainMaxLayers];
+    const CUtensorMap* maps;         // device array: [2l] W_l K-major (fwd), [2l+1] W_l MN-major (dgrad), [2L] X
+    const float* W;                  // weight arena (bias reads)
+    float* act[kChainMaxLayers + 1]; // act[0] = stage input, act[l] = output of layer l  ([all rows, ld])
+    float* dz[kChainMaxLayers + 1];  // dz[l] = gradient w.r.t. the pre-activation of layer l (dz[0]: stage input grad)
+    int act_ld[kChainMaxLayers + 1];
+    const float* target;             // [all rows, ldt] one-hot targets (last stage)
+    int ldt;
+    float* probs;                    // [all rows, ldp]
+    int ldp;
+    float* loss;                     // [n_mubatches]
+    int mb_rows, n_pad, stages;
+    int kps;                         // 32-wide k-blocks per pipeline stage (one wait / one commit per stage)
+    int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
+    float inv_batch;
+    int do_fwd, do_loss, do_bwd, first_stage;
+    int dbg_flags;                   // experiments: 1 = skip global stores, 2 = skip smem stores (fwd epilogue)
+    unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only
+};
+struct ChainPlan {
+    ChainParams p;
+    CUtensorMap* maps_dev;
+    int grid, smem_bytes;
+};
+bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss);
+const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches);
+void chain_plan_free(ChainPlan* plan);
+cudaError_t chain_configure();
+cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream);
 
 // ---- small fused kernels --------------------------------------------------------------
 // logits[rows, cols] (ld) -> probs (nullable) ; training: dlogits (softmax-Jacobian x MSE

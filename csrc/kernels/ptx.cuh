@@ -162,6 +162,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, u
     d |= static_cast<uint64_t>(1) << 61;   // SWIZZLE_128B_BASE32B
     return d;
 }
+// Descriptor = (hi << 32) | lo.  Within one k-block only the start address (lo[13:0]) moves, so the
+// issue loop builds lo/hi once and then steps lo by a constant - the uniform datapath that feeds
+// UTCHMMA is slow (each dependent op ~10+ cycles), so every op removed from the issue loop counts.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate, M x N tile.
 __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (1u << 4)                 // D format  = F32

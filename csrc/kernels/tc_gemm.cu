@@ -86,11 +86,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
+        // converged warp; one elect.sync-chosen lane issues (no ELECT/BRA.U.ANY uniformization loops)
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (kb / p.stages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 const uint32_t b_dst = a_dst + kABytes;
@@ -108,11 +109,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+        {
             const uint32_t idesc = umma_idesc_tf32(kBlockM, p.block_n, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            const uint32_t a_hi = A_MN ? umma_desc_hi(512u, 1u) : umma_desc_hi(1024u, 2u);
+            const uint32_t b_hi = B_MN ? umma_desc_hi(512u, 1u) : umma_desc_hi(1024u, 2u);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (kb / p.stages) & 1;
@@ -120,17 +124,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t a_src = smem_base + s * stage_bytes;
                 const uint32_t b_src = a_src + kABytes;
+                // descriptors: built once per k-block, stepped by a constant per UMMA_K = 8 slice
+                const uint32_t a_lo = A_MN ? umma_desc_lo(a_src, kPanelBytes) : umma_desc_lo(a_src, 16u);
+                const uint32_t b_lo = B_MN ? umma_desc_lo(b_src, kPanelBytes) : umma_desc_lo(b_src, 16u);
+                constexpr uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);
+                constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {         // UMMA_K = 8 for tf32
-                    const uint64_t adesc = A_MN ? umma_desc_mn_sw128_32b(a_src + k4 * 1024u, kPanelBytes, 512u)
-                                                : umma_desc_sw128(a_src + k4 * 32u, 16u, 1024u);
-                    const uint64_t bdesc = B_MN ? umma_desc_mn_sw128_32b(b_src + k4 * 1024u, kPanelBytes, 512u)
-                                                : umma_desc_sw128(b_src + k4 * 32u, 16u, 1024u);
-                    umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi), idesc,
+                                  (kb | k4) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar(s));                // smem stage free once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
                 }
-                umma_commit(empty_bar(s));                // smem stage free once these MMAs retire
+                __syncwarp();
             }
-            umma_commit(tmem_full_bar);                   // accumulator complete
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
@@ -301,6 +309,10 @@ static const char* make_tmap(CUtensorMap* map, const float* base, int inner, int
 // MN-major operand map ([rows(K) x 32 mn] panels) for other translation units (fused_dp.cu)
 const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int outer, int ld) {
     return make_tmap(map, base, inner, outer, ld, 32, true);
+}
+
+const char* make_tmap_k(CUtensorMap* map, const float* base, int inner, int outer, int ld, int box_outer) {
+    return make_tmap(map, base, inner, outer, ld, box_outer, false);
 }
 
 static int round_up_i(int x, int m) { return (x + m - 1) / m * m; }

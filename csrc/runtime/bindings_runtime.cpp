@@ -1,5 +1,6 @@
 // pybind11 face of the native runtime: NCCL communicators + PipeEngine.
 #include <torch/extension.h>
+#include <pybind11/stl.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <nccl.h>
 
@@ -129,6 +130,7 @@ public:
     void run() { engine_->run(); }
     void synchronize() { engine_->synchronize(); }
     float last_loss() { return engine_->last_loss(); }
+    float prev_loss() { return engine_->prev_loss(); }
     int count_correct() { return engine_->count_correct(); }
     void reset_correct() { engine_->reset_correct(); }
     torch::Tensor act(int mu, int l) {
@@ -149,6 +151,7 @@ public:
     int64_t graph_nodes() { return engine_->graph_nodes(); }
     int64_t main_stream() { return reinterpret_cast<int64_t>(engine_->main_stream()); }
     std::string describe() { return engine_->describe(); }
+    std::vector<unsigned long long> chain_timeline() { return engine_->chain_timeline(); }
 
 private:
     torch::Tensor weights_, grads_;
@@ -180,6 +183,7 @@ void bind_runtime(py::module_& m) {
         .def("run", &PyEngine::run)
         .def("synchronize", &PyEngine::synchronize)
         .def("last_loss", &PyEngine::last_loss)
+        .def("prev_loss", &PyEngine::prev_loss)
         .def("count_correct", &PyEngine::count_correct)
         .def("reset_correct", &PyEngine::reset_correct)
         .def("act", &PyEngine::act)
@@ -188,7 +192,8 @@ void bind_runtime(py::module_& m) {
         .def("kernels_per_step", &PyEngine::kernels_per_step)
         .def("graph_nodes", &PyEngine::graph_nodes)
         .def("main_stream", &PyEngine::main_stream)
-        .def("describe", &PyEngine::describe);
+        .def("describe", &PyEngine::describe)
+        .def("chain_timeline", &PyEngine::chain_timeline);
 }
 
 }  // namespace ssb

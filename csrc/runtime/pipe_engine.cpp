@@ -35,7 +35,7 @@ static constexpr int kFusedDpMaxCtas = 120;
 PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, int64_t arena_numel)
     : cfg_(cfg), W_(weights), G_(grads), arena_numel_(arena_numel), L_((int)cfg.layers.size()) {
     n_mu_streams_ = std::max(1, std::min(cfg_.n_mu, 4));
-    n_w_streams_ = std::max(1, std::min(L_, 4));
+    n_w_streams_ = std::max(1, std::min(L_, 8));        // one stream per layer's wgrad when possible
     if (const char* e = getenv("SSB_MU_STREAMS")) n_mu_streams_ = std::max(1, std::min(atoi(e), std::max(1, cfg_.n_mu)));
     if (const char* e = getenv("SSB_W_STREAMS")) n_w_streams_ = std::max(1, atoi(e));
     const int n_streams = 1 + n_mu_streams_ + n_w_streams_ + 2;
@@ -43,15 +43,26 @@ PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, in
     s_dp_ = s_comm_ + 1;
     streams_.resize(n_streams);
     for (auto& s : streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy_[i], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
+    }
     alloc_buffers();
 }
 
 PipeEngine::~PipeEngine() {
     cudaDeviceSynchronize();
-    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-    if (graph_) cudaGraphDestroy(graph_);
+    for (int i = 0; i < 2; ++i) {
+        if (graph_exec_sets_[i]) cudaGraphExecDestroy(graph_exec_sets_[i]);
+        if (graph_sets_[i]) cudaGraphDestroy(graph_sets_[i]);
+        cudaEventDestroy(ev_copy_[i]);
+        cudaEventDestroy(ev_done_[i]);
+    }
+    cudaStreamDestroy(copy_stream_);
     for (auto e : events_) cudaEventDestroy(e);
     for (auto s : streams_) cudaStreamDestroy(s);
+    for (auto& cp : chain_plans_) chain_plan_free(&cp);
     for (auto p : owned_) cudaFree(p);
     if (loss_host_) cudaFreeHost(loss_host_);
 }
@@ -69,12 +80,16 @@ void PipeEngine::alloc_buffers() {
         return p;
     };
     // stage input of all micro-batches is ONE buffer so a step needs a single (2-D) copy
-    x_stage_ = dalloc((size_t)M * mb * act_ld_[0]);
     y_ld_ = round_up(cfg_.out_dim, 8);
-    y_stage_ = dalloc((size_t)M * mb * y_ld_);
+    for (int set = 0; set < 2; ++set) {
+        x_stage_sets_[set] = dalloc((size_t)M * mb * act_ld_[0]);
+        y_stage_sets_[set] = dalloc((size_t)M * mb * y_ld_);
+    }
+    x_stage_ = x_stage_sets_[0];
+    y_stage_ = y_stage_sets_[0];
     loss_dev_ = dalloc(std::max(M, 16));
-    CUDA_CHECK(cudaMallocHost(&loss_host_, sizeof(float) * std::max(M, 16)));
-    for (int i = 0; i < std::max(M, 16); ++i) loss_host_[i] = 0.f;
+    CUDA_CHECK(cudaMallocHost(&loss_host_, 2 * sizeof(float) * std::max(M, 16)));   // one slot per staging set
+    for (int i = 0; i < 2 * std::max(M, 16); ++i) loss_host_[i] = 0.f;
     {
         int* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, 64));
@@ -104,6 +119,15 @@ void PipeEngine::alloc_buffers() {
     }
 }
 
+// Point the planner at one of the two input-staging sets (stage input = act[.][0], targets).
+void PipeEngine::select_set(int set) {
+    cur_set_ = set;
+    x_stage_ = x_stage_sets_[set];
+    y_stage_ = y_stage_sets_[set];
+    act_all_[0] = x_stage_;
+    for (int mu = 0; mu < cfg_.n_mu; ++mu) act_[mu][0] = act_all_[0] + (size_t)mu * cfg_.mb_rows * act_ld_[0];
+}
+
 int PipeEngine::new_event() {
     cudaEvent_t e;
     CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -120,6 +144,48 @@ int PipeEngine::emit_record(int stream) {
     op.kind = OP_RECORD; op.stream = stream; op.event = new_event();
     ops_.push_back(op);
     return op.event;
+}
+
+// One launch that walks micro-batches [mu_base, mu_base + n_mu) through the whole stage
+// (csrc/kernels/mlp_chain.cu).  Returns the op index.
+int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd) {
+    ChainParams cp{};
+    cp.n_layers = L_;
+    for (int l = 0; l < L_; ++l) {
+        const LayerSpec& ls = cfg_.layers[l];
+        cp.layers[l].in = ls.in; cp.layers[l].out = ls.out; cp.layers[l].relu = ls.relu; cp.layers[l].ldw = ls.ld;
+        cp.layers[l].w_off = ls.offset;
+    }
+    cp.W = W_;
+    for (int l = 0; l <= L_; ++l) {
+        cp.act[l] = act_all_[l];
+        cp.dz[l] = cfg_.training ? dz_all_[l] : nullptr;
+        cp.act_ld[l] = act_ld_[l];
+    }
+    cp.target = y_stage_; cp.ldt = y_ld_;
+    cp.probs = probs_all_; cp.ldp = act_ld_[L_];
+    cp.loss = loss_dev_;
+    cp.mb_rows = cfg_.mb_rows; cp.mu_base = mu_base;
+    cp.inv_batch = 1.0f / (float)cfg_.global_batch;
+    cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
+    cp.dbg = nullptr;
+    cp.dbg_flags = getenv("SSB_CHAIN_FLAGS") ? atoi(getenv("SSB_CHAIN_FLAGS")) : 0;
+    if (getenv("SSB_CHAIN_TIMELINE")) {
+        if (!chain_dbg_) {
+            CUDA_CHECK(cudaMalloc(&chain_dbg_, 3 * 256 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMemset(chain_dbg_, 0, 3 * 256 * sizeof(unsigned long long)));
+            owned_.push_back(chain_dbg_);
+        }
+        cp.dbg = chain_dbg_;
+    }
+    ChainPlan plan;
+    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu);
+    if (err) throw std::runtime_error(std::string("PipeEngine chain plan: ") + err);
+    chain_plans_.push_back(plan);
+    Op op;
+    op.kind = OP_CHAIN; op.stream = stream; op.gemm = (int)chain_plans_.size() - 1; op.mu = mu_base;
+    ops_.push_back(op);
+    return (int)ops_.size() - 1;
 }
 
 void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
@@ -157,12 +223,33 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         if (op >= I_RECV_ACT && op <= I_SEND_GRAD) has_comm = true;
     }
     coalesced_ = !has_comm && !getenv("SSB_NO_COALESCE");
-    if (coalesced_) {
-        build_coalesced();
-        finish_build();
-        return;
+    {
+        ChainLayer cl[kChainMaxLayers];
+        const int nl = std::min(L_, (int)kChainMaxLayers);
+        for (int l = 0; l < nl; ++l) { cl[l].in = cfg_.layers[l].in; cl[l].out = cfg_.layers[l].out; }
+        chain_ok_ = L_ >= 1 && L_ <= kChainMaxLayers && !getenv("SSB_NO_CHAIN") &&
+                    chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0);
     }
+    instrs_ = instrs;
+    mu_of_ = mu_of;
+    // Two complete plans, one per input-staging buffer: step i reads staging set i % 2 while the copy
+    // stream already fills the other set for step i + 1.
+    for (int set = 0; set < 2; ++set) {
+        select_set(set);
+        ops_.clear();
+        if (coalesced_) build_coalesced();
+        else plan_per_mubatch();
+        ops_sets_[set] = std::move(ops_);
+        ops_.clear();
+    }
+    finish_build();
+}
 
+void PipeEngine::plan_per_mubatch() {
+    const std::vector<std::tuple<int, int, int>>& instrs = instrs_;
+    const std::vector<int>& mu_of = mu_of_;
+    const int M = cfg_.n_mu, mb = cfg_.mb_rows, n = (int)instrs.size();
+    const bool first = cfg_.is_first, last = cfg_.is_last;
     std::vector<bool> started(streams_.size(), false);
     started[0] = true;
     Op begin;
@@ -367,10 +454,9 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
     if (cfg_.training && last) {
         Op cp;
-        cp.kind = OP_MEMCPY_LOSS; cp.stream = 0;
+        cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
         ops_.push_back(cp);
     }
-    finish_build();
 }
 
 // Stage without pipeline communication (pp == 1): micro-batches are independent until the
@@ -399,32 +485,44 @@ void PipeEngine::build_coalesced() {
     auto use = [&](int s) { if (!started[s]) { emit_wait(s, ev_begin); started[s] = true; } };
     auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
 
-    for (int l = 1; l <= L_; ++l) {
-        const LayerSpec& ls = cfg_.layers[l - 1];
-        GemmPlan g;
-        check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_all_[l - 1], act_ld_[l - 1], act_all_[l], act_ld_[l], rows, ls.in, ls.out,
-                            Wl(l) + ls.in, ls.ld, ls.relu));
-        add_gemm(g, 0, l);
+    const bool chain = chain_ok_;
+    if (chain) {
+        // forward + loss head (+ whole dgrad chain when training) of every micro-batch in ONE launch
+        add_chain(0, 0, M, true, true, cfg_.training != 0);
+        if (!cfg_.training) {
+            Op am;
+            am.kind = OP_ARGMAX; am.stream = 0;
+            am.a = probs_all_; am.lda = act_ld_[L_]; am.b = y_stage_; am.ldb = y_ld_; am.rows = rows; am.cols = cfg_.out_dim;
+            ops_.push_back(am);
+            return;
+        }
+    } else {
+        for (int l = 1; l <= L_; ++l) {
+            const LayerSpec& ls = cfg_.layers[l - 1];
+            GemmPlan g;
+            check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_all_[l - 1], act_ld_[l - 1], act_all_[l], act_ld_[l], rows, ls.in, ls.out,
+                                Wl(l) + ls.in, ls.ld, ls.relu));
+            add_gemm(g, 0, l);
+        }
+        if (!cfg_.training) {
+            Op sm_op;
+            sm_op.kind = OP_SOFTMAX; sm_op.stream = 0;
+            sm_op.a = act_all_[L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_all_; sm_op.ldb = act_ld_[L_];
+            sm_op.rows = rows; sm_op.cols = cfg_.out_dim; sm_op.n = mb;
+            ops_.push_back(sm_op);
+            Op am;
+            am.kind = OP_ARGMAX; am.stream = 0;
+            am.a = probs_all_; am.lda = act_ld_[L_]; am.b = y_stage_; am.ldb = y_ld_; am.rows = rows; am.cols = cfg_.out_dim;
+            ops_.push_back(am);
+            return;
+        }
+        Op lh;
+        lh.kind = OP_LOSS_HEAD; lh.stream = 0;
+        lh.a = act_all_[L_]; lh.lda = act_ld_[L_]; lh.b = y_stage_; lh.ldb = y_ld_; lh.c = probs_all_; lh.ldc = act_ld_[L_];
+        lh.d = dz_all_[L_]; lh.ldd = act_ld_[L_]; lh.rows = rows; lh.cols = cfg_.out_dim;
+        lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = 0; lh.n = mb;
+        ops_.push_back(lh);
     }
-    if (!cfg_.training) {
-        Op sm_op;
-        sm_op.kind = OP_SOFTMAX; sm_op.stream = 0;
-        sm_op.a = act_all_[L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_all_; sm_op.ldb = act_ld_[L_];
-        sm_op.rows = rows; sm_op.cols = cfg_.out_dim; sm_op.n = mb;
-        ops_.push_back(sm_op);
-        Op am;
-        am.kind = OP_ARGMAX; am.stream = 0;
-        am.a = probs_all_; am.lda = act_ld_[L_]; am.b = y_stage_; am.ldb = y_ld_; am.rows = rows; am.cols = cfg_.out_dim;
-        ops_.push_back(am);
-        return;
-    }
-    Op lh;
-    lh.kind = OP_LOSS_HEAD; lh.stream = 0;
-    lh.a = act_all_[L_]; lh.lda = act_ld_[L_]; lh.b = y_stage_; lh.ldb = y_ld_; lh.c = probs_all_; lh.ldc = act_ld_[L_];
-    lh.d = dz_all_[L_]; lh.ldd = act_ld_[L_]; lh.rows = rows; lh.cols = cfg_.out_dim;
-    lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = 0; lh.n = mb;
-    ops_.push_back(lh);
-
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
     int ev_bump = -1;
@@ -441,7 +539,7 @@ void PipeEngine::build_coalesced() {
         const LayerSpec& ls = cfg_.layers[l - 1];
         const int ev_dz = emit_record(0);
         int ev_dg = -1;
-        if (l > 1) {
+        if (l > 1 && !chain) {
             const float* mask = cfg_.layers[l - 2].relu ? act_all_[l - 1] : nullptr;
             GemmPlan g;
             check(gemm_plan_dgrad(&g, Wl(l), ls.ld, dz_all_[l], act_ld_[l], dz_all_[l - 1], act_ld_[l - 1], rows, ls.in, ls.out,
@@ -499,16 +597,16 @@ void PipeEngine::build_coalesced() {
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
     Op cp;
-    cp.kind = OP_MEMCPY_LOSS; cp.stream = 0;
+    cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
     ops_.push_back(cp);
 }
 
 void PipeEngine::finish_build() {
     kernels_per_step_ = 0;
-    for (auto& op : ops_) {
+    for (auto& op : ops_sets_[0]) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
-            op.kind == OP_BUMP_EPOCH)
+            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -516,14 +614,17 @@ void PipeEngine::finish_build() {
     // kernel attributes are configured up front (never inside a capture); communicators are
     // warmed up by their creator.  No eager pass here: a training step mutates the weights.
     CUDA_CHECK(gemm_configure());
+    if (!chain_plans_.empty()) CUDA_CHECK(chain_configure());
     if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
     if (cfg_.use_graph) {
-        CUDA_CHECK(cudaStreamBeginCapture(streams_[0], cudaStreamCaptureModeThreadLocal));
-        walk(true);
-        CUDA_CHECK(cudaStreamEndCapture(streams_[0], &graph_));
-        CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+        for (int set = 0; set < 2; ++set) {
+            CUDA_CHECK(cudaStreamBeginCapture(streams_[0], cudaStreamCaptureModeThreadLocal));
+            walk(set);
+            CUDA_CHECK(cudaStreamEndCapture(streams_[0], &graph_sets_[set]));
+            CUDA_CHECK(cudaGraphInstantiate(&graph_exec_sets_[set], graph_sets_[set], 0));
+        }
         size_t nn = 0;
-        CUDA_CHECK(cudaGraphGetNodes(graph_, nullptr, &nn));
+        CUDA_CHECK(cudaGraphGetNodes(graph_sets_[0], nullptr, &nn));
         graph_nodes_ = (int64_t)nn;
     }
 }
@@ -561,43 +662,69 @@ void PipeEngine::exec(const Op& op) {
             NCCL_CHECK(ncclGroupEnd());
             break;
         }
+        case OP_CHAIN: CUDA_CHECK(chain_launch(chain_plans_[op.gemm], st)); break;
         case OP_FUSED_DP: CUDA_CHECK(launch_fused_wgrad_dp(dp_plans_[op.gemm], st)); break;
         case OP_DP_REDUCE: CUDA_CHECK(launch_dp_reduce_sgd(dp_plans_[op.gemm], st)); break;
         case OP_BUMP_EPOCH: CUDA_CHECK(launch_bump_epoch(dp_ctx_->epoch_ptr(), st)); break;
         case OP_MEMCPY_LOSS:
-            CUDA_CHECK(cudaMemcpyAsync(loss_host_, loss_dev_, sizeof(float) * cfg_.n_mu, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(op.a, loss_dev_, sizeof(float) * cfg_.n_mu, cudaMemcpyDeviceToHost, st));
             break;
         default: throw std::runtime_error("PipeEngine: bad op");
     }
 }
 
-void PipeEngine::walk(bool) {
-    for (const auto& op : ops_) exec(op);
+void PipeEngine::walk(int set) {
+    for (const auto& op : ops_sets_[set]) exec(op);
 }
 
+// Inputs of step i go into staging set i % 2 on the COPY stream; the compute graph of that set waits
+// for the copy, and the next copy into the same set waits until that graph finished reading it.  The
+// host enqueues step i + 1's copy while step i still computes, so H2D traffic hides behind compute.
 void PipeEngine::stage_inputs(const float* x, const float* y, bool from_host) {
+    const int set = fill_set_;
     const size_t rows = (size_t)cfg_.n_mu * cfg_.mb_rows;
     const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, ev_done_[set], 0));
     if (x != nullptr && cfg_.is_first)
-        CUDA_CHECK(cudaMemcpy2DAsync(x_stage_, (size_t)act_ld_[0] * 4, x, (size_t)cfg_.in_dim * 4, (size_t)cfg_.in_dim * 4, rows,
-                                     kind, streams_[0]));
+        CUDA_CHECK(cudaMemcpy2DAsync(x_stage_sets_[set], (size_t)act_ld_[0] * 4, x, (size_t)cfg_.in_dim * 4, (size_t)cfg_.in_dim * 4,
+                                     rows, kind, copy_stream_));
     if (y != nullptr && cfg_.is_last)
-        CUDA_CHECK(cudaMemcpy2DAsync(y_stage_, (size_t)y_ld_ * 4, y, (size_t)cfg_.out_dim * 4, (size_t)cfg_.out_dim * 4, rows,
-                                     kind, streams_[0]));
+        CUDA_CHECK(cudaMemcpy2DAsync(y_stage_sets_[set], (size_t)y_ld_ * 4, y, (size_t)cfg_.out_dim * 4, (size_t)cfg_.out_dim * 4,
+                                     rows, kind, copy_stream_));
+    CUDA_CHECK(cudaEventRecord(ev_copy_[set], copy_stream_));
+    staged_ = true;
 }
 
 void PipeEngine::run() {
     if (!built_) throw std::runtime_error("PipeEngine::run before build");
-    if (graph_exec_) CUDA_CHECK(cudaGraphLaunch(graph_exec_, streams_[0]));
-    else walk(false);
+    const int set = fill_set_;
+    if (staged_) CUDA_CHECK(cudaStreamWaitEvent(streams_[0], ev_copy_[set], 0));
+    if (graph_exec_sets_[set]) CUDA_CHECK(cudaGraphLaunch(graph_exec_sets_[set], streams_[0]));
+    else walk(set);
+    CUDA_CHECK(cudaEventRecord(ev_done_[set], streams_[0]));
+    run_set_ = set;
+    if (staged_) fill_set_ ^= 1;
+    staged_ = false;
 }
 
 void PipeEngine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(streams_[0])); }
 
 float PipeEngine::last_loss() {
     synchronize();
+    const float* h = loss_host_ + run_set_ * std::max(cfg_.n_mu, 16);
     float s = 0.f;
-    for (int i = 0; i < cfg_.n_mu; ++i) s += loss_host_[i];
+    for (int i = 0; i < cfg_.n_mu; ++i) s += h[i];
+    return s;
+}
+
+// Loss of the step BEFORE the most recently launched one: waits only for that step's event, so the
+// GPU queue stays non-empty (H2D of step i+1 / compute of step i / D2H of step i-1 overlap).
+float PipeEngine::prev_loss() {
+    const int set = run_set_ ^ 1;
+    CUDA_CHECK(cudaEventSynchronize(ev_done_[set]));
+    const float* h = loss_host_ + set * std::max(cfg_.n_mu, 16);
+    float s = 0.f;
+    for (int i = 0; i < cfg_.n_mu; ++i) s += h[i];
     return s;
 }
 
@@ -609,10 +736,19 @@ int PipeEngine::count_correct() {
 }
 void PipeEngine::reset_correct() { CUDA_CHECK(cudaMemsetAsync(correct_dev_, 0, sizeof(int), streams_[0])); }
 
+std::vector<unsigned long long> PipeEngine::chain_timeline() {
+    std::vector<unsigned long long> v(3 * 256, 0);
+    if (chain_dbg_) {
+        synchronize();
+        CUDA_CHECK(cudaMemcpy(v.data(), chain_dbg_, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    return v;
+}
+
 std::string PipeEngine::describe() const {
     std::ostringstream os;
     os << "PipeEngine(stage " << cfg_.stage << "/" << cfg_.n_stages << ", layers=" << L_ << ", mb_rows=" << cfg_.mb_rows
-       << ", n_mu=" << cfg_.n_mu << ", ops=" << ops_.size() << ", kernels/step=" << kernels_per_step_
+       << ", n_mu=" << cfg_.n_mu << ", ops=" << ops_sets_[0].size() << ", kernels/step=" << kernels_per_step_
        << ", graph_nodes=" << graph_nodes_ << ", streams=" << streams_.size() << ", events=" << events_.size() << ")";
     return os.str();
 }

@@ -40,7 +40,7 @@ struct LayerSpec {
 
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
-    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH
+    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -97,7 +97,8 @@ public:
     void stage_inputs(const float* x, const float* y, bool from_host);
     void run();                       // one step (graph launch or eager plan walk) on the main stream
     void synchronize();
-    float last_loss();                // sum of the micro-batch losses of the most recent completed step
+    float last_loss();                // sum of the micro-batch losses of the most recent step (synchronizes)
+    float prev_loss();                // loss of the step before the most recently launched one (pipelined readback)
     int count_correct();              // inference: # argmax matches accumulated since reset
     void reset_correct();
 
@@ -112,18 +113,22 @@ public:
     int64_t kernels_per_step() const { return kernels_per_step_; }
     int64_t graph_nodes() const { return graph_nodes_; }
     bool coalesced() const { return coalesced_; }
+    bool uses_chain() const { return chain_ok_; }
     cudaStream_t main_stream() { return streams_[0]; }
     const EngineConfig& config() const { return cfg_; }
     std::string describe() const;
+    std::vector<unsigned long long> chain_timeline();   // SSB_CHAIN_TIMELINE=1: globaltimer stamps of the chain kernel
 
 private:
     void alloc_buffers();
     void build_coalesced();
+    void plan_per_mubatch();
+    void select_set(int set);
     void finish_build();
     int new_event();
     void emit_wait(int stream, int ev);
     int emit_record(int stream);
-    void walk(bool capturing);
+    void walk(int set);
     void exec(const Op& op);
 
     EngineConfig cfg_;
@@ -145,10 +150,22 @@ private:
     std::vector<cudaEvent_t> events_;
     std::vector<GemmPlan> gemms_;
     std::vector<FusedDpPlan> dp_plans_;
+    std::vector<ChainPlan> chain_plans_;
+    bool chain_ok_ = false;
+    unsigned long long* chain_dbg_ = nullptr;
+    int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd);
     DpContext* dp_ctx_ = nullptr;
     std::vector<Op> ops_;
-    cudaGraph_t graph_ = nullptr;
-    cudaGraphExec_t graph_exec_ = nullptr;
+    std::vector<Op> ops_sets_[2];
+    cudaGraph_t graph_sets_[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec_sets_[2] = {nullptr, nullptr};
+    float *x_stage_sets_[2] = {nullptr, nullptr}, *y_stage_sets_[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t ev_copy_[2], ev_done_[2];
+    int fill_set_ = 0, run_set_ = 0, cur_set_ = 0;
+    bool staged_ = false;
+    std::vector<std::tuple<int, int, int>> instrs_;
+    std::vector<int> mu_of_;
     int64_t kernels_per_step_ = 0, graph_nodes_ = 0;
     int kernels_extra_ = 0;
     ncclComm_t pp_comm_ = nullptr, dp_comm_ = nullptr;

@@ -211,13 +211,29 @@ class Trainer:
         self.schedule = cls(n_mubatches, pp, self.pp_comm.Get_rank())
         self.engine = self.worker.engine_for(self.schedule)
         self.is_first, self.is_last = self.schedule.is_first_stage, self.schedule.is_last_stage
+        self._steps = 0
 
     def step_async(self, x_host, y_host):
         self.engine.stage_inputs(x_host if self.is_first else None, y_host if self.is_last else None)
         self.engine.run()
+        self._steps += 1
 
     def step(self, x_host, y_host):
+        """Run one step and return its loss (synchronises with the device)."""
         self.step_async(x_host, y_host)
+        return self.engine.last_loss() if self.is_last else None
+
+    def step_pipelined(self, x_host, y_host):
+        """Enqueue one step (H2D of its inputs, compute, D2H of its loss) and return the loss of the
+        PREVIOUS step, read from pinned host memory after waiting only for that step's event.  The
+        device queue never drains: copy-in of step i+1, compute of step i and read-back of step i-1
+        overlap.  The first call returns None; ``flush()`` returns the final loss."""
+        self.step_async(x_host, y_host)
+        if not self.is_last or self._steps < 2:
+            return None
+        return self.engine.prev_loss()
+
+    def flush(self):
         return self.engine.last_loss() if self.is_last else None
 
     def loss(self):

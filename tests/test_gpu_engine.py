@@ -56,9 +56,26 @@ def test_engine_matches_cpu_training(sched, use_graph):
         # compare the UPDATE (3 SGD steps): TF32 products => a few % in norm on the gradients
         assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < 5e-2
         assert _frob(pg.data.cpu(), pc.data) < 5e-2
-    # pp == 1: micro-batches are horizontally fused -> 7 fwd + 6 dgrad (layer 1 skipped) + 7 wgrad
-    # (SGD fused into the wgrad epilogue) + 1 loss head (one CTA per micro-batch)
-    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 21
+    # pp == 1, narrow layers: ONE chain launch (fwd + loss head + dgrad chain, one CTA per micro-batch)
+    # + 7 wgrad GEMMs with the SGD update fused into their epilogue
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 8
+
+
+def test_engine_layerwise_path_matches_cpu(monkeypatch):
+    """Chain kernel disabled: per-layer launches over all micro-batches (the path wide layers use):
+    7 fwd + 1 loss head + 6 dgrad + 7 wgrad(+SGD)."""
+    from shallowspeed_b200.layers import MLP
+    from shallowspeed_b200.pipe import GPipeSchedule
+
+    monkeypatch.setenv("SSB_NO_CHAIN", "1")
+    out = _setup(GPipeSchedule)
+    (mc, lc, _), (mg, lg, wg) = out["cpu"], out["cuda"]
+    for a, b in zip(lc, lg):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a))
+    init = MLP(SIZES, 0, 1, 128)
+    for p0, pc, pg in zip(init.parameters(), mc.parameters(), mg.parameters()):
+        assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < 5e-2
+    assert wg.kernels_per_step(GPipeSchedule(4, 1, 0)) == 21
 
 
 @pytest.mark.parametrize("sched", ["naive", "pipedream"])
