@@ -41,6 +41,13 @@ __device__ __forceinline__ float ld_cg_f(const float* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long gtime_dp() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DPDBG(idx) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[idx] = gtime_dp(); } while (0)
+
 struct TileCoord {
     int t, mt, nt, owner, slot;
 };
@@ -60,43 +67,75 @@ __device__ __forceinline__ float* stage_slot(const DpPeers& peers, const DpLayer
 // ---- phase B: the owner reduces one tile in rank order, applies SGD, publishes the weights
 // Executed by `nthreads` threads (tid in [0, nthreads)), all of which must call it.
 __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& p, const TileCoord& tc, uint32_t epoch,
-                                     int tid, int nthreads, int bar_id) {
+                                     int tid, int nthreads, int bar_id, int part = 0, int nparts = 1) {
     const int me = p.rank;
     // wait until every replica's partial of this tile has landed in my staging memory
     if (tid < p.dp) wait_flag_ge(peers.arrive[me] + (int64_t)tid * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    if (tid == 0) DPDBG(5);
 
     const int m0 = tc.mt * (int)kBlockM, n0 = tc.nt * p.block_n;
     const int f4_per_row = p.block_n / 4;
-    const int total_f4 = (int)kBlockM * f4_per_row;
     const float* st0 = stage_slot(peers, p, me, 0, tc.slot, epoch);
     const int n_pub = p.one_shot ? 1 : p.dp;              // one-shot: every replica updates only its own W
     const bool vec_ok = (p.ldw % 4) == 0;
-    for (int f = tid; f < total_f4; f += nthreads) {
-        const int r = f / f4_per_row, c4 = f % f4_per_row;
-        const int m = m0 + r, n = n0 + 4 * c4;
-        if (m >= p.m_total || n >= p.n_total) continue;
-        float4 sum = ld_cg_f4(st0 + (int64_t)r * p.block_n + 4 * c4);
-        for (int s = 1; s < p.dp; ++s) {          // fixed order 0,1,..,dp-1 => deterministic, replica-independent
-            const float4 v = ld_cg_f4(st0 + (int64_t)s * p.stage_src_stride + (int64_t)r * p.block_n + 4 * c4);
-            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    // batches of kU float4 per thread: issue every staging / weight load of the batch first, then
+    // reduce in fixed rank order - otherwise each iteration pays a full L2 round trip
+    constexpr int kU = 4;
+    const int rows_valid = min((int)kBlockM, p.m_total - m0);
+    // this CTA's share of the tile rows (helper CTAs split the reduce)
+    const int rows_per = (rows_valid + nparts - 1) / nparts;
+    const int r_begin = min(rows_valid, part * rows_per), r_end = min(rows_valid, r_begin + rows_per);
+    const int limit_f4 = r_end * f4_per_row;                // rows beyond m_total never need work
+    for (int f0 = r_begin * f4_per_row + tid; f0 < limit_f4; f0 += nthreads * kU) {
+        float4 part[kMaxDp > 4 ? 4 : kMaxDp][kU];           // up to 4 replicas buffered; more are streamed below
+        float4 wv[kU];
+        const int nbuf = p.dp < 4 ? p.dp : 4;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int f = f0 + u * nthreads;
+            const int r = f / f4_per_row, c4 = f % f4_per_row;
+            const int n = n0 + 4 * c4;
+            const bool ok = f < limit_f4 && n < p.n_total;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                part[s][u] = (ok && s < nbuf) ? ld_cg_f4(st0 + (int64_t)s * p.stage_src_stride + (int64_t)r * p.block_n + 4 * c4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t woff = p.w_offset + (int64_t)(m0 + r) * p.ldw + n;
+            wv[u] = (ok && vec_ok && n + 3 < p.n_total) ? *reinterpret_cast<const float4*>(peers.W[me] + woff)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const int64_t woff = p.w_offset + (int64_t)m * p.ldw + n;
-        if (vec_ok && n + 3 < p.n_total) {
-            float4 w = *reinterpret_cast<const float4*>(peers.W[me] + woff);
-            w.x -= p.lr * sum.x; w.y -= p.lr * sum.y; w.z -= p.lr * sum.z; w.w -= p.lr * sum.w;
-            if (n_pub == 1) *reinterpret_cast<float4*>(peers.W[me] + woff) = w;
-            else for (int r2 = 0; r2 < p.dp; ++r2) *reinterpret_cast<float4*>(peers.W[r2] + woff) = w;   // publish to all replicas
-        } else {
-            const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
-            for (int e = 0; e < 4 && n + e < p.n_total; ++e) {
-                const float w = peers.W[me][woff + e] - p.lr * sv[e];
-                if (n_pub == 1) peers.W[me][woff + e] = w;
-                else for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][woff + e] = w;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int f = f0 + u * nthreads;
+            const int r = f / f4_per_row, c4 = f % f4_per_row;
+            const int m = m0 + r, n = n0 + 4 * c4;
+            if (f >= limit_f4 || n >= p.n_total) continue;
+            float4 sum = part[0][u];
+#pragma unroll
+            for (int s = 1; s < 4; ++s)
+                if (s < nbuf) { sum.x += part[s][u].x; sum.y += part[s][u].y; sum.z += part[s][u].z; sum.w += part[s][u].w; }
+            for (int s = 4; s < p.dp; ++s) {                  // fixed order 0,1,..,dp-1 => deterministic, replica-independent
+                const float4 v = ld_cg_f4(st0 + (int64_t)s * p.stage_src_stride + (int64_t)r * p.block_n + 4 * c4);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const int64_t woff = p.w_offset + (int64_t)m * p.ldw + n;
+            if (vec_ok && n + 3 < p.n_total) {
+                float4 w = wv[u];
+                w.x -= p.lr * sum.x; w.y -= p.lr * sum.y; w.z -= p.lr * sum.z; w.w -= p.lr * sum.w;
+                if (n_pub == 1) *reinterpret_cast<float4*>(peers.W[me] + woff) = w;
+                else for (int r2 = 0; r2 < p.dp; ++r2) *reinterpret_cast<float4*>(peers.W[r2] + woff) = w;   // publish to all replicas
+            } else {
+                const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+                for (int e = 0; e < 4 && n + e < p.n_total; ++e) {
+                    const float w = peers.W[me][woff + e] - p.lr * sv[e];
+                    if (n_pub == 1) peers.W[me][woff + e] = w;
+                    else for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][woff + e] = w;
+                }
             }
         }
     }
-    if (tc.nt == 0) {   // bias gradient rides at the end of the slot
+    if (tc.nt == 0 && part == 0) {   // bias gradient rides at the end of the slot
         for (int r = tid; r < (int)kBlockM; r += nthreads) {
             const int m = m0 + r;
             if (m >= p.m_total) continue;
@@ -113,7 +152,7 @@ __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& 
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
     if (tid == 0) {
         __threadfence_system();                            // one cumulative fence after the CTA barrier
-        for (int r2 = 0; r2 < p.dp; ++r2) st_release_sys(peers.done[r2] + p.tile_flag_base + tc.t, epoch);
+        for (int r2 = 0; r2 < p.dp; ++r2) st_relaxed_sys(peers.done[r2] + p.tile_flag_base + tc.t, epoch);
     }
 }
 
@@ -135,16 +174,26 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
     const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+    if (p.helpers > 1 && (blockIdx.x % p.helpers) != 0) {
+        // helper CTA (one-shot layers, one tile per CTA group): no GEMM - just its share of the reduce
+        const uint32_t epoch_h = *reinterpret_cast<const volatile uint32_t*>(p.epoch_ptr);
+        const TileCoord tc = tile_coord(p, blockIdx.x / p.helpers);
+        dp_owner_reduce_tile(peers, p, tc, epoch_h, threadIdx.x, kThreads, 1, blockIdx.x % p.helpers, p.helpers);
+        return;
+    }
+    const int cta = p.helpers > 1 ? blockIdx.x / p.helpers : blockIdx.x;      // tile-group index
+    const int n_cta = p.helpers > 1 ? gridDim.x / p.helpers : gridDim.x;
     const uint32_t b_bytes = p.block_n * 128u;
     const uint32_t stage_bytes = kABytes + b_bytes;
-    const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+    const uint32_t tile_bytes_k = kBlockM * ((uint32_t)p.block_n * 4u + 16u);
+    const uint32_t bar_base = smem_base + p.stages * stage_bytes + tile_bytes_k;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
     const uint32_t tmem_empty_bar = tmem_full_bar + 8u;
     const uint32_t tmem_slot = tmem_empty_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + 8u * (2 * p.stages + 2));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + tile_bytes_k + 8u * (2 * p.stages + 2));
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
 
@@ -172,7 +221,7 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0) {
         {   // converged warp, elect.sync-chosen issuing lane
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = cta; t < num_tiles; t += n_cta) {
                 const int m0 = (t / p.n_tiles_n) * kBlockM, n0 = (t % p.n_tiles_n) * p.block_n;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
@@ -224,6 +273,7 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int etid = (warp - 2) * 32 + lane;                 // 0..127 among the epilogue threads
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         // ---------------- phase A: compute every tile, push the partial to its owner
+        if (etid == 0) DPDBG(0);
         int it = 0, tile_i = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
             const TileCoord tc = tile_coord(p, t);
@@ -247,16 +297,46 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             mbar_wait(tmem_full_bar, tile_i & 1);
             tc_fence_after();
+            if (etid == 0 && tile_i == 0) DPDBG(1);
             const int n_dst = p.one_shot ? p.dp : 1;
+            // TMEM (thread = row) -> padded smem tile -> row-contiguous 512-byte warp stores: each P2P store
+            // instruction carries one full contiguous row segment over NVLink instead of 32 scattered 16-byte pieces
+            const uint32_t pitch = (uint32_t)p.block_n * 4u + 16u;
+            uint8_t* tile = smem_gen + p.stages * stage_bytes;
             for (int c = 0; c < p.block_n; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + c, v);
-                for (int d = 0; d < n_dst; ++d) {                 // two-shot: the owner only; one-shot: every replica
-                    const int dst_rank = p.one_shot ? d : tc.owner;
-                    float* drow = stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch) + (int64_t)m_local * p.block_n;
 #pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4)
-                        *reinterpret_cast<float4*>(drow + c + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                for (int g4 = 0; g4 < 4; ++g4)
+                    *reinterpret_cast<float4*>(tile + (size_t)m_local * pitch + (size_t)(c + 4 * g4) * 4) =
+                        make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);           // accumulator drained: the next tile's MMA may start
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.bulk_push) {
+                // one TMA bulk copy per row and destination, issued by the thread that wrote the row
+                fence_proxy_async_smem();
+                for (int d = 0; d < n_dst; ++d) {
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    float* dst = stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch);
+                    bulk_copy_s2g(dst + (int64_t)m_local * p.block_n, smem_base + p.stages * stage_bytes + (uint32_t)m_local * pitch,
+                                  (uint32_t)p.block_n * 4u);
+                }
+                tma_store_commit();
+                tma_store_wait_all();
+                asm volatile("fence.proxy.async;" ::: "memory");
+            } else {
+                const int ew = warp - 2;                          // 0..3
+                const int f4_per_row = p.block_n / 4;
+                for (int d = 0; d < n_dst; ++d) {
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    float* dst = stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch);
+                    for (int r = ew; r < (int)kBlockM; r += 4)
+                        for (int c4 = lane; c4 < f4_per_row; c4 += 32)
+                            *reinterpret_cast<float4*>(dst + (int64_t)r * p.block_n + 4 * c4) =
+                                *reinterpret_cast<const float4*>(tile + (size_t)r * pitch + (size_t)c4 * 16);
                 }
             }
             if (tc.nt == 0)
@@ -264,26 +344,27 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const int dst_rank = p.one_shot ? d : tc.owner;
                     stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch)[(int64_t)kBlockM * p.block_n + m_local] = dbsum;
                 }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);           // MMA of the next tile may overwrite TMEM
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (etid == 0) {
+                if (tile_i == 0) DPDBG(2);
                 __threadfence_system();                           // partial visible system-wide before the flag(s)
+                if (tile_i == 0) DPDBG(3);
                 for (int d = 0; d < n_dst; ++d) {
                     const int dst_rank = p.one_shot ? d : tc.owner;
-                    st_release_sys(peers.arrive[dst_rank] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+                    st_relaxed_sys(peers.arrive[dst_rank] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
                 }
             }
         }
         // ---------------- phase B: reduce + SGD + publish the tiles this replica owns
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (etid == 0) DPDBG(4);
+        for (int t = cta; t < num_tiles; t += n_cta) {
             const TileCoord tc = tile_coord(p, t);
-            if (p.one_shot || tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1);
+            if (p.one_shot || tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1, 0, p.helpers > 1 ? p.helpers : 1);
         }
         // ---------------- phase C: wait for the owners of my other tiles
+        if (etid == 0) DPDBG(6);
         if (etid == 0 && !p.one_shot) {
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = cta; t < num_tiles; t += n_cta) {
                 const TileCoord tc = tile_coord(p, t);
                 if (tc.owner != p.rank) dp_wait_tile_done(peers, p, tc, epoch);
             }
@@ -337,7 +418,7 @@ __global__ void __launch_bounds__(128, 1) dp_reduce_sgd_kernel(const DpLayerPara
         if (tid == 0) {
             __threadfence_system();
             for (int d = 0; d < n_dst; ++d)
-                st_release_sys(peers.arrive[p.one_shot ? d : tc.owner] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+                st_relaxed_sys(peers.arrive[p.one_shot ? d : tc.owner] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
         }
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -360,6 +441,8 @@ const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int out
 void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, int* n_tiles_n, int64_t* slots, int64_t* slot_floats_out,
                        int one_shot) {
     *block_n = in >= 128 ? 128 : (in + 31) / 32 * 32;
+    // latency-bound one-shot layers: narrow tiles => 4x more CTAs share the push and the reduce
+    if (one_shot && !getenv("SSB_DP_WIDE_TILES")) *block_n = 32;
     *n_tiles_m = (out + (int)kBlockM - 1) / (int)kBlockM;
     *n_tiles_n = (in + *block_n - 1) / *block_n;
     const int64_t tiles = (int64_t)*n_tiles_m * *n_tiles_n;
@@ -380,13 +463,20 @@ const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const fl
     }
     const int num_kb = (rows + (int)kBlockK - 1) / (int)kBlockK;
     const int stage_bytes = (int)kABytes + p.block_n * 128;
-    int stages = 200 * 1024 / stage_bytes;
+    const int tile_bytes = (int)kBlockM * (p.block_n * 4 + 16);   // padded transpose tile for coalesced P2P stores
+    int stages = (200 * 1024 - tile_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages > std::max(num_kb, 2)) stages = std::max(num_kb, 2);
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + 1024 + 8 * (2 * stages + 3) + 16;
+    plan->smem_bytes = stages * stage_bytes + tile_bytes + 1024 + 8 * (2 * stages + 3) + 16;
     const int tiles = p.n_tiles_m * p.n_tiles_n;
     plan->grid = tiles < max_ctas ? tiles : max_ctas;
+    // small one-shot layers: spend idle SMs on the reduce (helper CTAs split the tile rows)
+    p.helpers = 1;
+    if (dZ != nullptr && p.one_shot && tiles <= 16 && getenv("SSB_DP_HELPERS")) {   // experimental, off by default
+        p.helpers = 4;
+        plan->grid = tiles * p.helpers;
+    }
     return nullptr;
 }
 

@@ -95,6 +95,9 @@ struct DpLayerParams {
     // one NVLink hop instead of two).  Staging is double-buffered by epoch parity (stage_parity_stride).
     int one_shot;
     int64_t stage_parity_stride;
+    int helpers;                     // CTAs per tile: CTA 0 computes + pushes, all of them share the reduce rows
+    int bulk_push;                   // 1: push tiles with cp.async.bulk (TMA engine), 0: coalesced st.global
+    unsigned long long* dbg;         // optional: 8 globaltimer stamps of CTA 0 (phase timeline)
 };
 struct FusedDpPlan {
     CUtensorMap tmA, tmB;

@@ -84,6 +84,10 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t sme
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
                  : "memory");
 }
+// contiguous bulk copy shared -> global (the destination may be peer memory mapped over NVLink)
+__device__ __forceinline__ void bulk_copy_s2g(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -186,6 +190,11 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, uint
 // ------------------------------------------------------------------ system-scope flags (peer memory)
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// flag store AFTER an explicit system-scope fence (fence + relaxed store = release pattern; a
+// st.release.sys per flag would pay one more ~3 us NVLink-draining fence each)
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;

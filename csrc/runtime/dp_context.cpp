@@ -102,6 +102,9 @@ DpLayerParams DpContext::layer_params(int i) const {
     p.epoch_ptr = epoch_;
     p.G = nullptr; p.ldg = g.ld;
     p.one_shot = g.one_shot;
+    p.dbg = nullptr;
+    p.helpers = 1;
+    p.bulk_push = getenv("SSB_DP_BULK") ? atoi(getenv("SSB_DP_BULK")) : 1;   // TMA bulk copies to peer memory (verified on NVLink)
     p.stage_parity_stride = stage_parity_stride_;
     return p;
 }

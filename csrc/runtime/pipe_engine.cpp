@@ -172,8 +172,8 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.dbg_flags = getenv("SSB_CHAIN_FLAGS") ? atoi(getenv("SSB_CHAIN_FLAGS")) : 0;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {
-            CUDA_CHECK(cudaMalloc(&chain_dbg_, 3 * 256 * sizeof(unsigned long long)));
-            CUDA_CHECK(cudaMemset(chain_dbg_, 0, 3 * 256 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMemset(chain_dbg_, 0, 4 * 256 * sizeof(unsigned long long)));
             owned_.push_back(chain_dbg_);
         }
         cp.dbg = chain_dbg_;
@@ -557,8 +557,16 @@ void PipeEngine::build_coalesced() {
             emit_wait(sdp, ev_dz);
             if (ev_dg >= 0) emit_wait(sdp, ev_dg);
             FusedDpPlan fp;
-            check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, dp_ctx_->layer_params(l - 1),
-                                dp_ctx_->peers(), kFusedDpMaxCtas));
+            DpLayerParams lp = dp_ctx_->layer_params(l - 1);
+            if (getenv("SSB_CHAIN_TIMELINE")) {
+                if (!chain_dbg_) {
+                    CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
+                    CUDA_CHECK(cudaMemset(chain_dbg_, 0, 4 * 256 * sizeof(unsigned long long)));
+                    owned_.push_back(chain_dbg_);
+                }
+                lp.dbg = chain_dbg_ + 3 * 256 + 8 * l;
+            }
+            check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, lp, dp_ctx_->peers(), kFusedDpMaxCtas));
             dp_plans_.push_back(fp);
             Op fo;
             fo.kind = OP_FUSED_DP; fo.stream = sdp; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = l;
@@ -737,7 +745,7 @@ int PipeEngine::count_correct() {
 void PipeEngine::reset_correct() { CUDA_CHECK(cudaMemsetAsync(correct_dev_, 0, sizeof(int), streams_[0])); }
 
 std::vector<unsigned long long> PipeEngine::chain_timeline() {
-    std::vector<unsigned long long> v(3 * 256, 0);
+    std::vector<unsigned long long> v(4 * 256, 0);
     if (chain_dbg_) {
         synchronize();
         CUDA_CHECK(cudaMemcpy(v.data(), chain_dbg_, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
