@@ -332,24 +332,36 @@ void PipeEngine::plan_per_mubatch() {
                 const int s = sm(mu);
                 use(s);
                 if (ev_in[mu] >= 0) { emit_wait(s, ev_in[mu]); ev_in[mu] = -1; }
-                for (int l = 1; l <= L_; ++l) {
-                    const LayerSpec& ls = cfg_.layers[l - 1];
-                    GemmPlan g;
-                    check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_[mu][l - 1], act_ld_[l - 1], act_[mu][l], act_ld_[l], mb,
-                                        ls.in, ls.out, Wl(l) + ls.in, ls.ld, ls.relu));
-                    add_gemm(g, s, l, mu);
-                }
-                if (!cfg_.training && last) {
-                    Op sm_op;
-                    sm_op.kind = OP_SOFTMAX; sm_op.stream = s;
-                    sm_op.a = act_[mu][L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_[mu]; sm_op.ldb = act_ld_[L_];
-                    sm_op.rows = mb; sm_op.cols = cfg_.out_dim;
-                    ops_.push_back(sm_op);
-                    Op am;
-                    am.kind = OP_ARGMAX; am.stream = s;
-                    am.a = probs_[mu]; am.lda = act_ld_[L_]; am.b = y_stage_ + (size_t)mu * mb * y_ld_; am.ldb = y_ld_;
-                    am.rows = mb; am.cols = cfg_.out_dim;
-                    ops_.push_back(am);
+                if (chain_ok_) {
+                    // whole stage forward (+ loss head on the last stage) of this micro-batch in one launch
+                    add_chain(s, mu, 1, true, last, false);
+                    if (!cfg_.training && last) {
+                        Op am;
+                        am.kind = OP_ARGMAX; am.stream = s;
+                        am.a = probs_[mu]; am.lda = act_ld_[L_]; am.b = y_stage_ + (size_t)mu * mb * y_ld_; am.ldb = y_ld_;
+                        am.rows = mb; am.cols = cfg_.out_dim;
+                        ops_.push_back(am);
+                    }
+                } else {
+                    for (int l = 1; l <= L_; ++l) {
+                        const LayerSpec& ls = cfg_.layers[l - 1];
+                        GemmPlan g;
+                        check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_[mu][l - 1], act_ld_[l - 1], act_[mu][l], act_ld_[l], mb,
+                                            ls.in, ls.out, Wl(l) + ls.in, ls.ld, ls.relu));
+                        add_gemm(g, s, l, mu);
+                    }
+                    if (!cfg_.training && last) {
+                        Op sm_op;
+                        sm_op.kind = OP_SOFTMAX; sm_op.stream = s;
+                        sm_op.a = act_[mu][L_]; sm_op.lda = act_ld_[L_]; sm_op.b = probs_[mu]; sm_op.ldb = act_ld_[L_];
+                        sm_op.rows = mb; sm_op.cols = cfg_.out_dim;
+                        ops_.push_back(sm_op);
+                        Op am;
+                        am.kind = OP_ARGMAX; am.stream = s;
+                        am.a = probs_[mu]; am.lda = act_ld_[L_]; am.b = y_stage_ + (size_t)mu * mb * y_ld_; am.ldb = y_ld_;
+                        am.rows = mb; am.cols = cfg_.out_dim;
+                        ops_.push_back(am);
+                    }
                 }
                 ev_fwd[mu] = emit_record(s);
                 break;
@@ -360,48 +372,75 @@ void PipeEngine::plan_per_mubatch() {
                 const int s = sm(mu);
                 use(s);
                 if (ev_gout[mu] >= 0) { emit_wait(s, ev_gout[mu]); ev_gout[mu] = -1; }
-                if (last) {
-                    Op lh;
-                    lh.kind = OP_LOSS_HEAD; lh.stream = s;
-                    lh.a = act_[mu][L_]; lh.lda = act_ld_[L_];
-                    lh.b = y_stage_ + (size_t)mu * mb * y_ld_; lh.ldb = y_ld_;
-                    lh.c = probs_[mu]; lh.ldc = act_ld_[L_];
-                    lh.d = dz_[mu][L_]; lh.ldd = act_ld_[L_];
-                    lh.rows = mb; lh.cols = cfg_.out_dim; lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = mu;
-                    ops_.push_back(lh);
-                } else if (L_ > 0 && cfg_.layers[L_ - 1].relu) {
-                    Op rm;
-                    rm.kind = OP_RELU_MASK; rm.stream = s;
-                    rm.a = dz_[mu][L_]; rm.lda = act_ld_[L_]; rm.b = act_[mu][L_]; rm.ldb = act_ld_[L_];
-                    rm.rows = mb; rm.cols = cfg_.layers[L_ - 1].out;
-                    ops_.push_back(rm);
-                }
-                for (int l = L_; l >= 1; --l) {
-                    const LayerSpec& ls = cfg_.layers[l - 1];
-                    const int ev_dz = emit_record(s);
-                    const int w = sw(l);
-                    use(w);
-                    emit_wait(w, ev_dz);
-                    GemmPlan g;
-                    check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
-                                          ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
-                    add_gemm(g, w, l, mu);
-                    first_write[l] = false;
-                    if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
-                        const int ev_g = emit_record(w);
-                        use(s_dp_);
-                        emit_wait(s_dp_, ev_g);
-                        Op ar;
-                        ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
-                        ops_.push_back(ar);
+                if (chain_ok_) {
+                    // dZ_L (from the loss head at forward time, or received from the next stage) -> ReLU mask ->
+                    // the whole dgrad chain in one launch; then one wave of weight-gradient GEMMs
+                    add_chain(s, mu, 1, false, false, true);
+                    const int ev_dz_all = emit_record(s);
+                    for (int l = L_; l >= 1; --l) {
+                        const LayerSpec& ls = cfg_.layers[l - 1];
+                        const int w = sw(l);
+                        use(w);
+                        emit_wait(w, ev_dz_all);
+                        GemmPlan g;
+                        check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
+                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                        add_gemm(g, w, l, mu);
+                        first_write[l] = false;
+                        if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
+                            const int ev_g = emit_record(w);
+                            use(s_dp_);
+                            emit_wait(s_dp_, ev_g);
+                            Op ar;
+                            ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
+                            ops_.push_back(ar);
+                        }
+                        if (final_bwd && cfg_.dp_mode == 2) pending_dp.push_back({l, emit_record(w)});
                     }
-                    if (final_bwd && cfg_.dp_mode == 2) pending_dp.push_back({l, emit_record(w)});
-                    if (l > 1 || !first) {
-                        const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
-                        GemmPlan g2;
-                        check(gemm_plan_dgrad(&g2, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
-                                              ls.out, mask, act_ld_[l - 1]));
-                        add_gemm(g2, s, l, mu);
+                } else {
+                    if (last) {
+                        Op lh;
+                        lh.kind = OP_LOSS_HEAD; lh.stream = s;
+                        lh.a = act_[mu][L_]; lh.lda = act_ld_[L_];
+                        lh.b = y_stage_ + (size_t)mu * mb * y_ld_; lh.ldb = y_ld_;
+                        lh.c = probs_[mu]; lh.ldc = act_ld_[L_];
+                        lh.d = dz_[mu][L_]; lh.ldd = act_ld_[L_];
+                        lh.rows = mb; lh.cols = cfg_.out_dim; lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = mu;
+                        ops_.push_back(lh);
+                    } else if (L_ > 0 && cfg_.layers[L_ - 1].relu) {
+                        Op rm;
+                        rm.kind = OP_RELU_MASK; rm.stream = s;
+                        rm.a = dz_[mu][L_]; rm.lda = act_ld_[L_]; rm.b = act_[mu][L_]; rm.ldb = act_ld_[L_];
+                        rm.rows = mb; rm.cols = cfg_.layers[L_ - 1].out;
+                        ops_.push_back(rm);
+                    }
+                    for (int l = L_; l >= 1; --l) {
+                        const LayerSpec& ls = cfg_.layers[l - 1];
+                        const int ev_dz = emit_record(s);
+                        const int w = sw(l);
+                        use(w);
+                        emit_wait(w, ev_dz);
+                        GemmPlan g;
+                        check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
+                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                        add_gemm(g, w, l, mu);
+                        first_write[l] = false;
+                        if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
+                            const int ev_g = emit_record(w);
+                            use(s_dp_);
+                            emit_wait(s_dp_, ev_g);
+                            Op ar;
+                            ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
+                            ops_.push_back(ar);
+                        }
+                        if (final_bwd && cfg_.dp_mode == 2) pending_dp.push_back({l, emit_record(w)});
+                        if (l > 1 || !first) {
+                            const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
+                            GemmPlan g2;
+                            check(gemm_plan_dgrad(&g2, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
+                                                  ls.out, mask, act_ld_[l - 1]));
+                            add_gemm(g2, s, l, mu);
+                        }
                     }
                 }
                 ev_bwd[mu] = emit_record(s);

@@ -78,14 +78,17 @@ def test_engine_layerwise_path_matches_cpu(monkeypatch):
     assert wg.kernels_per_step(GPipeSchedule(4, 1, 0)) == 21
 
 
+@pytest.mark.parametrize("chain", [True, False])
 @pytest.mark.parametrize("sched", ["naive", "pipedream"])
-def test_engine_per_microbatch_path_matches_cpu(sched, monkeypatch):
+def test_engine_per_microbatch_path_matches_cpu(sched, chain, monkeypatch):
     """Same check with horizontal fusion disabled: every micro-batch is its own chain of
     launches on its own stream (the path pipeline stages with p2p comm use)."""
     from shallowspeed_b200.layers import MLP
     from shallowspeed_b200.pipe import SCHEDULE_NAME_TO_CLS
 
     monkeypatch.setenv("SSB_NO_COALESCE", "1")
+    if not chain:
+        monkeypatch.setenv("SSB_NO_CHAIN", "1")
     out = _setup(SCHEDULE_NAME_TO_CLS[sched])
     (mc, lc, _), (mg, lg, wg) = out["cpu"], out["cuda"]
     for a, b in zip(lc, lg):
@@ -93,7 +96,9 @@ def test_engine_per_microbatch_path_matches_cpu(sched, monkeypatch):
     init = MLP(SIZES, 0, 1, 128)
     for p0, pc, pg in zip(init.parameters(), mc.parameters(), mg.parameters()):
         assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < 5e-2
-    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 4 * (7 + 6 + 7) + 4 + 1
+    # chain: per micro-batch 1 fwd(+loss) chain + 1 bwd chain + 7 wgrad, + 1 SGD; layer-wise: 7 + 1 + 6 + 7 each
+    expect = 4 * (1 + 1 + 7) + 1 if chain else 4 * (7 + 6 + 7) + 4 + 1
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == expect
 
 
 def test_engine_is_bit_deterministic():
