@@ -42,6 +42,14 @@ def parse():
     ap.add_argument("--schedule", default="naive")
     ap.add_argument("--comm", choices=["fused", "nccl"], default="fused")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--precision", choices=["fp32", "tf32"], default="fp32",
+                    help="fp32 = 3xTF32 tensor-core products (fp32-equivalent, the reference's contract); tf32 = single pass")
+    ap.add_argument("--pp", type=int, default=1, help="pipeline stages (dp = gpus / pp)")
+    ap.add_argument("--n-mubatches", type=int, default=N_MUBATCHES)
+    ap.add_argument("--hidden", type=int, default=None)
+    ap.add_argument("--n-layers", type=int, default=None, help="with --hidden: 784 -> hidden x (n-1) -> 10")
+    ap.add_argument("--global-batch", type=int, default=None, help="override the global batch size")
+    ap.add_argument("--seed-mode", default="shape")
     ap.add_argument("--pool-batches", type=int, default=352, help="distinct batches in the input pool (352 x 401 KB = 141 MB > L2)")
     return ap.parse_args()
 
@@ -57,7 +65,16 @@ def relaunch_under_torchrun(args):
 
 
 def global_batch(args):
-    return PER_GPU_BATCH * args.gpus if args.scaling == "weak" else PER_GPU_BATCH
+    if args.global_batch:
+        return args.global_batch
+    dp = args.gpus // args.pp
+    return PER_GPU_BATCH * dp if args.scaling == "weak" else PER_GPU_BATCH
+
+
+def layer_sizes(args):
+    if args.hidden or args.n_layers:
+        return [784] + [args.hidden or 128] * ((args.n_layers or 7) - 1) + [10]
+    return list(LAYER_SIZES)
 
 
 # ----------------------------------------------------------------------------------------
@@ -119,27 +136,32 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-        grid = ProcessGrid(world, 1, rank)
+        grid = ProcessGrid(world // args.pp, args.pp, rank)
         dp_comm, pp_comm = make_torch_comms(grid)
     else:
         grid, dp_comm, pp_comm = ProcessGrid(1, 1, 0), None, None
+    dp = world // args.pp
 
     gbs = global_batch(args)
-    local_bs = gbs // world
-    trainer = Trainer(LAYER_SIZES, global_batch_size=gbs, n_mubatches=N_MUBATCHES, lr=LR, schedule=args.schedule,
-                      dp_comm=dp_comm, pp_comm=pp_comm, grid=grid, comm_mode=args.comm, use_graph=not args.no_graph,
-                      device=dev)
+    local_bs = gbs // dp
+    sizes = layer_sizes(args)
+    trainer = Trainer(sizes, global_batch_size=gbs, n_mubatches=args.n_mubatches, lr=LR, schedule=args.schedule,
+                      dp_comm=dp_comm if dp > 1 else None, pp_comm=pp_comm if args.pp > 1 else None, grid=grid,
+                      comm_mode=args.comm, use_graph=not args.no_graph, device=dev, seed_mode=args.seed_mode,
+                      precision=args.precision)
     eng = trainer.engine
 
-    # input pools: this rank's shard of `pool` distinct global batches
+    # input pools: this replica's shard of `pool` distinct global batches
     pool = args.pool_batches
+    if len(sizes) > 9 or max(sizes[1:-1] or [0]) > 2048:
+        pool = min(pool, 16)                        # big models: the weights alone dwarf L2
     x, y = synthetic_mnist(n=pool * gbs)
-    xs = torch.from_numpy(x[rank::world].copy()).reshape(pool, local_bs, 784)
-    ys = torch.from_numpy(y[rank::world].copy()).reshape(pool, local_bs, 10)
+    xs = torch.from_numpy(x[grid.replica::dp].copy()).reshape(pool, local_bs, 784)
+    ys = torch.from_numpy(y[grid.replica::dp].copy()).reshape(pool, local_bs, 10)
     x_host, y_host = xs.pin_memory(), ys.pin_memory()
     x_dev, y_dev = xs.to(dev), ys.to(dev)
     h2d = x_host[0].numel() * 4 + y_host[0].numel() * 4
-    d2h = 4 * N_MUBATCHES
+    d2h = 4 * args.n_mubatches
 
     stream = torch.cuda.ExternalStream(eng.main_stream(), device=dev)
 
@@ -183,7 +205,7 @@ def run_ours(args):
     ms_dev, ms_e2e = max_over_ranks(ms_dev, dev), max_over_ranks(ms_e2e, dev)
     clocks = clk.summary()
 
-    if world > 1:   # replicas must still be bit-identical after the run
+    if dp > 1:   # replicas must still be bit-identical after the run
         from shallowspeed_b200.utils import assert_sync, get_model_hash
 
         trainer.synchronize()
@@ -196,18 +218,22 @@ def run_ours(args):
             "impl": "ours", "metric": "MLP training samples/sec (whole job)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "tf32 tensor-core products, fp32 storage + fp32 accumulate (reference contract: fp32)",
+            "dtype": ("fp32 (storage + accumulate fp32; products on tcgen05 as 3xTF32 = lo*hi + hi*lo + hi*hi, rel. error ~1e-6)"
+                      if args.precision == "fp32" else "tf32 (fp32 storage + accumulate, single-pass tf32 products)"),
             "data": "synthetic MNIST-shaped, random-init weights",
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": kps * args.steps,
             "clocks": clocks,
-            "config": {"model": "MLP 784-128-127-126-125-124-123-10", "global_batch": gbs, "per_gpu_batch": local_bs,
-                       "n_mubatches": N_MUBATCHES, "seq_len": None, "parallelism": f"dp{world}", "schedule": args.schedule,
-                       "dp_comm": args.comm if world > 1 else "none", "cuda_graph": not args.no_graph,
+            "config": {"model": "MLP " + "-".join(str(v) for v in (sizes if len(sizes) <= 9 else sizes[:2] + ["..."] + sizes[-2:])),
+                       "global_batch": gbs, "per_replica_batch": local_bs,
+                       "n_mubatches": args.n_mubatches, "seq_len": None,
+                       "parallelism": f"dp{dp}" + (f"xpp{args.pp}" if args.pp > 1 else ""), "schedule": args.schedule,
+                       "dp_comm": args.comm if dp > 1 else "none", "cuda_graph": not args.no_graph,
                        "kernels_per_step": kps, "graph_nodes": int(eng.graph_nodes()),
                        "l2": f"inputs cycle through a pool of {pool} distinct batches ({pool * h2d / 1e6:.0f} MB > 126 MB L2); "
                              "the 0.7 MB of weights are legitimately L2-resident across steps",
+                       "uses_chain_kernel": bool(eng.uses_chain()) if hasattr(eng, "uses_chain") else None,
                        "last_loss": losses[-1] if losses else None},
         }))
     if world > 1:

@@ -26,8 +26,28 @@ static void cuda_ok(cudaError_t e, const char* what) {
 static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
 // y[rows, out] = relu?(x @ W^T + b)
+static ssb::GemmLo make_lo(const c10::optional<Tensor>& a, const c10::optional<Tensor>& b, const c10::optional<Tensor>& out) {
+    ssb::GemmLo lo;
+    if (a.has_value() && b.has_value()) {
+        lo.A = a->data_ptr<float>();
+        lo.B = b->data_ptr<float>();
+        lo.out = out.has_value() ? out->data_ptr<float>() : nullptr;
+    }
+    return lo;
+}
+
+static void split_lo(const Tensor& x, Tensor& lo) {
+    TORCH_CHECK(x.is_cuda() && lo.is_cuda() && x.scalar_type() == torch::kFloat32 && lo.scalar_type() == torch::kFloat32);
+    TORCH_CHECK(x.storage().nbytes() > 0 && x.numel() == lo.numel());
+    c10::cuda::CUDAGuard guard(x.device());
+    // operates on the padded storage of 2-D views (same strides for x and lo)
+    const int64_t n = x.dim() == 2 ? x.size(0) * x.stride(0) : x.numel();
+    cuda_ok(ssb::launch_split_lo(x.data_ptr<float>(), lo.data_ptr<float>(), n, cur_stream()), "split_lo");
+}
+
 static void linear_fwd(const Tensor& x, const Tensor& W, const c10::optional<Tensor>& bias, int64_t bias_stride,
-                       bool relu, Tensor& y) {
+                       bool relu, Tensor& y, const c10::optional<Tensor>& W_lo, const c10::optional<Tensor>& x_lo,
+                       const c10::optional<Tensor>& y_lo) {
     check_mat(x, "x"); check_mat(W, "W"); check_mat(y, "y");
     const int rows = x.size(0), in = x.size(1), out = W.size(0);
     TORCH_CHECK(W.size(1) == in && y.size(0) == rows && y.size(1) == out, "linear_fwd: shape mismatch");
@@ -35,13 +55,15 @@ static void linear_fwd(const Tensor& x, const Tensor& W, const c10::optional<Ten
     ssb::GemmPlan plan;
     const char* err = ssb::gemm_plan_fwd(&plan, W.data_ptr<float>(), ld_of(W), x.data_ptr<float>(), ld_of(x),
                                          y.data_ptr<float>(), ld_of(y), rows, in, out,
-                                         bias.has_value() ? bias->data_ptr<float>() : nullptr, (int)bias_stride, relu);
+                                         bias.has_value() ? bias->data_ptr<float>() : nullptr, (int)bias_stride, relu,
+                                         make_lo(W_lo, x_lo, y_lo));
     TORCH_CHECK(err == nullptr, "linear_fwd: ", err ? err : "");
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_fwd launch");
 }
 
 // dx[rows, in] = (dz @ W) * (mask > 0)
-static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<Tensor>& mask, Tensor& dx) {
+static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<Tensor>& mask, Tensor& dx,
+                         const c10::optional<Tensor>& W_lo, const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& dx_lo) {
     check_mat(dz, "dz"); check_mat(W, "W"); check_mat(dx, "dx");
     const int rows = dz.size(0), out = dz.size(1), in = W.size(1);
     TORCH_CHECK(W.size(0) == out && dx.size(0) == rows && dx.size(1) == in, "linear_dgrad: shape mismatch");
@@ -51,14 +73,15 @@ static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<
     const char* err = ssb::gemm_plan_dgrad(&plan, W.data_ptr<float>(), ld_of(W), dz.data_ptr<float>(), ld_of(dz),
                                            dx.data_ptr<float>(), ld_of(dx), rows, in, out,
                                            mask.has_value() ? mask->data_ptr<float>() : nullptr,
-                                           mask.has_value() ? ld_of(*mask) : 0);
+                                           mask.has_value() ? ld_of(*mask) : 0, make_lo(W_lo, dz_lo, dx_lo));
     TORCH_CHECK(err == nullptr, "linear_dgrad: ", err ? err : "");
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_dgrad launch");
 }
 
 // G[out, in] (+)= dz^T @ x ; db[out] (+)= colsum(dz) ; optionally W -= lr * (G + ...)
 static void linear_wgrad(const Tensor& dz, const Tensor& x, Tensor& G, bool accumulate, const c10::optional<Tensor>& db,
-                         int64_t db_stride, const c10::optional<Tensor>& W, double lr, bool fuse_sgd) {
+                         int64_t db_stride, const c10::optional<Tensor>& W, double lr, bool fuse_sgd,
+                         const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& x_lo) {
     check_mat(dz, "dz"); check_mat(x, "x"); check_mat(G, "G");
     const int rows = dz.size(0), out = dz.size(1), in = x.size(1);
     TORCH_CHECK(x.size(0) == rows && G.size(0) == out && G.size(1) == in, "linear_wgrad: shape mismatch");
@@ -68,7 +91,7 @@ static void linear_wgrad(const Tensor& dz, const Tensor& x, Tensor& G, bool accu
                                            G.data_ptr<float>(), ld_of(G), rows, in, out, accumulate,
                                            db.has_value() ? db->data_ptr<float>() : nullptr, (int)db_stride,
                                            W.has_value() ? W->data_ptr<float>() : nullptr,
-                                           W.has_value() ? ld_of(*W) : 0, (float)lr, fuse_sgd);
+                                           W.has_value() ? ld_of(*W) : 0, (float)lr, fuse_sgd, make_lo(dz_lo, x_lo, c10::nullopt));
     TORCH_CHECK(err == nullptr, "linear_wgrad: ", err ? err : "");
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_wgrad launch");
 }
@@ -124,6 +147,7 @@ static void argmax_correct(const Tensor& pred, const Tensor& target, Tensor& cor
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "shallowspeed_b200 native module: sm_100a kernels + C++ pipeline runtime";
+    m.def("split_lo", &split_lo);
     m.def("linear_fwd", &linear_fwd);
     m.def("linear_dgrad", &linear_dgrad);
     m.def("linear_wgrad", &linear_wgrad);

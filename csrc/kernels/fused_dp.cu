@@ -165,6 +165,7 @@ __device__ __forceinline__ void dp_wait_tile_done(const DpPeers& peers, const Dp
 // =============================================================================================
 __global__ void __launch_bounds__(kThreads, 1)
 fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                       const DpLayerParams p, const DpPeers peers) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -184,7 +185,8 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int cta = p.helpers > 1 ? blockIdx.x / p.helpers : blockIdx.x;      // tile-group index
     const int n_cta = p.helpers > 1 ? gridDim.x / p.helpers : gridDim.x;
     const uint32_t b_bytes = p.block_n * 128u;
-    const uint32_t stage_bytes = kABytes + b_bytes;
+    const uint32_t half_bytes = kABytes + b_bytes;
+    const uint32_t stage_bytes = p.split ? 2u * half_bytes : half_bytes;
     const uint32_t tile_bytes_k = kBlockM * ((uint32_t)p.block_n * 4u + 16u);
     const uint32_t bar_base = smem_base + p.stages * stage_bytes + tile_bytes_k;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -235,6 +237,13 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         for (int i = 0; i < 4; ++i) tma_load_2d(a_dst + i * kPanelBytes, &tmA, full_bar(s), m0 + 32 * i, k0);
                         for (int j = 0; j < p.block_n / 32; ++j)
                             tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
+                        if (p.split) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                tma_load_2d(a_dst + half_bytes + i * kPanelBytes, &tmAlo, full_bar(s), m0 + 32 * i, k0);
+                            for (int j = 0; j < p.block_n / 32; ++j)
+                                tma_load_2d(b_dst + half_bytes + j * kPanelBytes, &tmBlo, full_bar(s), n0 + 32 * j, k0);
+                        }
                     }
                     __syncwarp();
                 }
@@ -256,6 +265,16 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const uint32_t a_src = smem_base + s * stage_bytes, b_src = a_src + kABytes;
                     const uint32_t a_lo = umma_desc_lo(a_src, kPanelBytes), b_lo = umma_desc_lo(b_src, kPanelBytes);
                     if (elect_one()) {
+                        if (p.split) {
+                            const uint32_t al = a_lo + (half_bytes >> 4), bl = b_lo + (half_bytes >> 4);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                umma_tf32(tmem_base, umma_desc_pack(al + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc,
+                                          (kb | k4) != 0 ? 1u : 0u);
+                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(bl + k4 * 64u, mn_hi), idesc, 1u);
+                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, 1u);
+                            }
+                        } else
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
                             umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc,
@@ -451,7 +470,7 @@ void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, in
 }
 
 const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const float* X, int ldx, int rows, const DpLayerParams& lp,
-                          const DpPeers& peers, int max_ctas) {
+                          const DpPeers& peers, int max_ctas, const float* dZ_lo, const float* X_lo) {
     *plan = FusedDpPlan{};
     plan->p = lp;
     plan->peers = peers;
@@ -460,9 +479,16 @@ const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const fl
     if (dZ != nullptr) {
         if (const char* e = make_tmap_mn(&plan->tmA, dZ, p.m_total, rows, lddz)) return e;
         if (const char* e = make_tmap_mn(&plan->tmB, X, p.n_total, rows, ldx)) return e;
+        plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
+        p.split = 0;
+        if (dZ_lo != nullptr && X_lo != nullptr) {
+            p.split = 1;
+            if (const char* e = make_tmap_mn(&plan->tmAlo, dZ_lo, p.m_total, rows, lddz)) return e;
+            if (const char* e = make_tmap_mn(&plan->tmBlo, X_lo, p.n_total, rows, ldx)) return e;
+        }
     }
     const int num_kb = (rows + (int)kBlockK - 1) / (int)kBlockK;
-    const int stage_bytes = (int)kABytes + p.block_n * 128;
+    const int stage_bytes = ((int)kABytes + p.block_n * 128) * (p.split ? 2 : 1);
     const int tile_bytes = (int)kBlockM * (p.block_n * 4 + 16);   // padded transpose tile for coalesced P2P stores
     int stages = (200 * 1024 - tile_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
@@ -487,7 +513,7 @@ cudaError_t launch_fused_wgrad_dp(const FusedDpPlan& plan, cudaStream_t stream) 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    fused_wgrad_dp_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.p, plan.peers);
+    fused_wgrad_dp_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmAlo, plan.tmBlo, plan.p, plan.peers);
     return cudaGetLastError();
 }
 cudaError_t fused_dp_configure() {

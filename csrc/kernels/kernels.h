@@ -42,10 +42,15 @@ struct GemmParams {
     int ldw;
     float lr;
     int fuse_sgd;
+    // fp32-equivalent mode (3xTF32): both operands come with a `lo` twin (x - trunc_tf32(x)); FWD/DGRAD
+    // also emit the lo twin of their output so the next GEMM can consume it
+    int split;
+    float* out_lo;
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
     CUtensorMap tmA, tmB, tmC;   // C: WGRAD output tile (G, or W when the SGD update is fused)
+    CUtensorMap tmAlo, tmBlo;    // lo twins of the operands (split mode)
     GemmParams p;
     int mode;
     dim3 grid;
@@ -57,13 +62,19 @@ struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B eac
 //   FWD:   W[out, in] (ldw), X[rows, in] (ldx)            -> Y[rows, out] (ldy)
 //   DGRAD: W[out, in] (ldw), dZ[rows, out] (lddz)         -> dX[rows, in] (lddx)
 //   WGRAD: dZ[rows, out] (lddz), X[rows, in] (ldx)        -> G[out, in] (ldg)
+// *_lo pointers: nullptr = plain TF32; non-null = 3xTF32 (twins share the layout of their tensor)
+struct GemmLo {
+    const float* A = nullptr;   // lo twin of the first operand  (W for fwd/dgrad, dZ for wgrad)
+    const float* B = nullptr;   // lo twin of the second operand (X for fwd, dZ for dgrad, X for wgrad)
+    float* out = nullptr;       // fwd/dgrad: where to write the lo twin of the output
+};
 const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* X, int ldx, float* Y, int ldy,
-                          int rows, int in, int out, const float* bias, int bias_stride, int relu);
+                          int rows, int in, int out, const float* bias, int bias_stride, int relu, GemmLo lo = GemmLo());
 const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float* dZ, int lddz, float* dX, int lddx,
-                            int rows, int in, int out, const float* mask, int ldmask);
+                            int rows, int in, int out, const float* mask, int ldmask, GemmLo lo = GemmLo());
 const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const float* X, int ldx, float* G, int ldg,
                             int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
-                            float lr, int fuse_sgd);
+                            float lr, int fuse_sgd, GemmLo lo = GemmLo());
 cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 cudaError_t gemm_configure();   // opt every instantiation into > 48 KB dynamic smem (call outside graph capture)
 int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)
@@ -95,12 +106,13 @@ struct DpLayerParams {
     // one NVLink hop instead of two).  Staging is double-buffered by epoch parity (stage_parity_stride).
     int one_shot;
     int64_t stage_parity_stride;
+    int split;                       // 3xTF32: lo twins of dZ / X are loaded too
     int helpers;                     // CTAs per tile: CTA 0 computes + pushes, all of them share the reduce rows
     int bulk_push;                   // 1: push tiles with cp.async.bulk (TMA engine), 0: coalesced st.global
     unsigned long long* dbg;         // optional: 8 globaltimer stamps of CTA 0 (phase timeline)
 };
 struct FusedDpPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmAlo, tmBlo;
     DpLayerParams p;
     DpPeers peers;
     int grid;
@@ -110,7 +122,8 @@ void dp_layer_geometry(int in, int out, int dp, int* block_n, int* n_tiles_m, in
                        int64_t* slot_floats, int one_shot);
 // dZ == nullptr: plan for dp_reduce_sgd (no GEMM)
 const char* fused_dp_plan(FusedDpPlan* plan, const float* dZ, int lddz, const float* X, int ldx, int rows,
-                          const DpLayerParams& lp, const DpPeers& peers, int max_ctas);
+                          const DpLayerParams& lp, const DpPeers& peers, int max_ctas, const float* dZ_lo = nullptr,
+                          const float* X_lo = nullptr);
 cudaError_t fused_dp_configure();
 cudaError_t launch_fused_wgrad_dp(const FusedDpPlan& plan, cudaStream_t stream);
 cudaError_t launch_dp_reduce_sgd(const FusedDpPlan& plan, cudaStream_t stream);
@@ -125,7 +138,11 @@ struct ChainLayer {
 struct ChainParams {
     int n_layers;
     ChainLayer layers[kChainMaxLayers];
-    const CUtensorMap* maps;         // device array: [2l] W_l K-major (fwd), [2l+1] W_l MN-major (dgrad), [2L] X
+    const CUtensorMap* maps;         // device array: [2l] W_l K-major (fwd), [2l+1] W_l MN-major (dgrad), [2L] X;
+                                     // split mode: the same 2L+1 maps for the lo twins follow at [2L+1 ..]
+    int split;                       // 3xTF32 (fp32-equivalent) products
+    float* act_lo[kChainMaxLayers + 1];   // lo twins written next to act / dz (consumed by the wgrad GEMMs)
+    float* dz_lo[kChainMaxLayers + 1];
     const float* W;                  // weight arena (bias reads)
     float* act[kChainMaxLayers + 1]; // act[0] = stage input, act[l] = output of layer l  ([all rows, ld])
     float* dz[kChainMaxLayers + 1];  // dz[l] = gradient w.r.t. the pre-activation of layer l (dz[0]: stage input grad)
@@ -149,7 +166,8 @@ struct ChainPlan {
     int grid, smem_bytes;
 };
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss);
-const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches);
+const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
+                       const float* W_lo = nullptr, const float* x_lo = nullptr);
 void chain_plan_free(ChainPlan* plan);
 cudaError_t chain_configure();
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream);
@@ -159,15 +177,18 @@ cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream);
 // grad, 1/batch_size inside) and loss_out[0] = sum((t-p)^2)/batch_size.
 cudaError_t launch_loss_head(const float* logits, int ldl, const float* target, int ldt, float* probs, int ldp,
                              float* dlogits, int ldd, float* loss_out, int rows, int cols, float inv_batch,
-                             cudaStream_t stream, int rows_per_mubatch = 0);   // >0: one CTA per micro-batch, loss_out[mu]
+                             cudaStream_t stream, int rows_per_mubatch = 0, float* dlogits_lo = nullptr);   // >0: one CTA per micro-batch, loss_out[mu]
 // generic softmax backward for the functional API: dz = p*up - p*sum(p*up)
 cudaError_t launch_softmax_grad(const float* logits, int ldl, const float* upstream, int ldu, float* dlogits, int ldd,
                                 int rows, int cols, cudaStream_t stream);
 // g[r, c] = y[r, c] > 0 ? g[r, c] : 0   (stage-boundary ReLU backward)
-cudaError_t launch_relu_mask(float* g, int ldg, const float* y, int ldy, int rows, int cols, cudaStream_t stream);
+cudaError_t launch_relu_mask(float* g, int ldg, const float* y, int ldy, int rows, int cols, cudaStream_t stream,
+                             float* g_lo = nullptr);   // g_lo: recomputed lo twin of the masked gradient
 cudaError_t launch_relu_fwd(const float* x, float* y, long n, cudaStream_t stream);
 // y = a * x + b * t  (mse grad: a=2/B, b=-2/B)
 cudaError_t launch_axpby(const float* x, const float* t, float* y, float a, float b, long n, cudaStream_t stream);
+// lo[i] = x[i] - trunc_tf32(x[i]) over a flat buffer (weights after the update, staged inputs)
+cudaError_t launch_split_lo(const float* x, float* lo, long n, cudaStream_t stream);
 // w -= lr * g over a flat arena
 cudaError_t launch_sgd(float* w, const float* g, float lr, long n, cudaStream_t stream);
 // correct[0] += #rows with argmax(pred) == argmax(target)

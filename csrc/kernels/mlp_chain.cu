@@ -66,22 +66,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     const int N = p.n_pad;                                   // UMMA N (rows of this micro-batch, padded to 16)
     const int row0 = (p.mu_base + (int)blockIdx.x) * p.mb_rows;                 // first global row of this micro-batch
     const uint32_t b_bytes = (uint32_t)N * 128u;             // one 32-feature panel of an activation tile
-    const uint32_t stage_bytes = (uint32_t)p.kps * (kABytes + b_bytes);   // kps A tiles, then kps X tiles (layer 1)
+    const uint32_t half_stage = (uint32_t)p.kps * (kABytes + b_bytes);    // kps A tiles, then kps X tiles (layer 1)
+    const uint32_t stage_bytes = p.split ? 2u * half_stage : half_stage;  // split: lo twins in the second half
     const uint32_t stage_b_off = (uint32_t)p.kps * kABytes;
     const uint32_t abuf_bytes = 4u * b_bytes;
+    const uint32_t n_abuf = p.split ? 4u : 2u;                            // hi ping-pong (+ lo ping-pong)
     const uint32_t abuf0 = smem_base + p.stages * stage_bytes;
-    const uint32_t bar_base = abuf0 + 2u * abuf_bytes;
+    const uint32_t lo_off = 2u * abuf_bytes;                              // lo tile of buffer b sits lo_off behind its hi tile
+    const uint32_t bar_base = abuf0 + n_abuf * abuf_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
     const uint32_t act_ready_bar = tmem_full_bar + 8u;
     const uint32_t tmem_slot = act_ready_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + 2u * abuf_bytes + 8u * (2 * p.stages + 2));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)N) tmem_cols <<= 1;
     // loss-head transpose scratch [N][kScratchLd] floats, behind the barriers (128 B further)
-    const uint32_t scratch_off = p.stages * stage_bytes + 2u * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
+    const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
 
     // number of backward GEMMs: layers L..lo (layer 1's dgrad is skipped on the first stage)
     const int bwd_lo = p.first_stage ? 2 : 1;
+    const int lo_base = 2 * L + 1;                           // index of the first lo-twin tensor map
 
     if (warp == 0) {
         // ============================================================ weight (and X) producer
@@ -125,11 +129,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (p.split ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
                                 tma_load_2d(a_dst + j * kABytes, p.maps + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                 if (with_x)
                                     tma_load_2d(a_dst + stage_b_off + j * b_bytes, p.maps + 2 * L, full_bar(s), (kb0 + j) * kBlockK, row0);
+                                if (p.split) {
+                                    tma_load_2d(a_dst + half_stage + j * kABytes, p.maps + lo_base + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
+                                    if (with_x)
+                                        tma_load_2d(a_dst + half_stage + stage_b_off + j * b_bytes, p.maps + lo_base + 2 * L, full_bar(s),
+                                                    (kb0 + j) * kBlockK, row0);
+                                }
                             }
                         }
                         __syncwarp();
@@ -145,12 +155,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes);
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (p.split ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j)
 #pragma unroll
-                                for (int i = 0; i < 4; ++i)
+                                for (int i = 0; i < 4; ++i) {
                                     tma_load_2d(a_dst + j * kABytes + i * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s), 32 * i,
                                                 (kb0 + j) * kBlockK);
+                                    if (p.split)
+                                        tma_load_2d(a_dst + half_stage + j * kABytes + i * kPanelBytes, p.maps + lo_base + 2 * (l - 1) + 1,
+                                                    full_bar(s), 32 * i, (kb0 + j) * kBlockK);
+                                }
                         }
                         __syncwarp();
                     }
@@ -185,10 +199,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             const uint32_t a_lo = a_mn ? umma_desc_lo(a_j, kPanelBytes) : umma_desc_lo(a_j, 16u);
                             const uint32_t b_lo = umma_desc_lo(b_j, 16u);
                             const uint32_t a_step = a_mn ? 64u : 2u;
+                            const uint32_t ah = a_mn ? mn_hi : k_hi, id = a_mn ? idesc_b : idesc_f;
+                            if (p.split) {                           // lo*hi + hi*lo + hi*hi (raw tiles are the hi parts)
+                                const uint32_t al_lo = a_lo + (half_stage >> 4);
+                                const uint32_t bl_lo = b_lo + ((b_from_stage ? half_stage : lo_off) >> 4);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    umma_tf32(tmem_base, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                              ((kb0 + j) | k4) != 0 ? 1u : 0u);
+                                    umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
+                                    umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id, 1u);
+                                }
+                            } else
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_mn ? mn_hi : k_hi),
-                                          umma_desc_pack(b_lo + k4 * 2u, k_hi), a_mn ? idesc_b : idesc_f,
+                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
                                           ((kb0 + j) | k4) != 0 ? 1u : 0u);
                         }
                         umma_commit(empty_bar(s));
@@ -228,6 +253,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         const int c_lo = 16 * ((n_chunks * half) / 2), c_hi = 16 * ((n_chunks * (half + 1)) / 2);
         int tmem_waits = 0;
         int wbuf = 0;                                        // activation buffer the NEXT epilogue writes
+        auto st_tile = [&](uint32_t dst, int n, int feat, float x) {   // operand tile(s) for the next GEMM
+            const uint32_t off = (dst - smem_base) + act_smem_off(n, feat, b_bytes);
+            *reinterpret_cast<float*>(smem_gen + off) = x;
+            if (p.split) *reinterpret_cast<float*>(smem_gen + off + lo_off) = tf32_lo(x);
+        };
         auto publish = [&]() {                               // smem tile complete -> MMA warp may read it
             if (threadIdx.x == 64) DBG(2, 2 * (tmem_waits - 1) + 1);
             fence_proxy_async_smem();
@@ -261,16 +291,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             if (ly.relu) x = fmaxf(x, 0.f);
                             x = m_ok ? x : 0.f;
                             const int n = c + j;
-                            *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, m, b_bytes)) = x;
+                            st_tile(dst, n, m, x);
                             if (single) keep[j] = x;
-                            else if (m_ok && n < p.mb_rows) gout[(int64_t)n * p.act_ld[l] + m] = x;
+                            else if (m_ok && n < p.mb_rows) {
+                                gout[(int64_t)n * p.act_ld[l] + m] = x;
+                                if (p.split) p.act_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + m] = tf32_lo(x);
+                            }
                         }
                     }
                     publish();
                     if (single && m_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c_lo + j < p.mb_rows) gout[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
+                            if (c_lo + j < p.mb_rows) {
+                                gout[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
+                                if (p.split) p.act_lo[l][(int64_t)(row0 + c_lo + j) * p.act_ld[l] + m] = tf32_lo(keep[j]);
+                            }
                     }
                     wbuf ^= 1;
                     if (l == 1) wbuf = 1;                    // layer 1 wrote abuf 0; layer 2 reads 0, writes 1
@@ -332,8 +368,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                             gout[(int64_t)n * p.act_ld[l] + k] = zr[k];
                                             p.probs[(int64_t)(row0 + n) * p.ldp + k] = ev[k];
                                             if (p.dz[l] != nullptr) p.dz[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = dzv;
+                                            if (p.split && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
                                         }
-                                        if (p.do_bwd) *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, k, b_bytes)) = dzv;
+                                        if (p.do_bwd) st_tile(dst, n, k, dzv);
                                     }
                                 }
                             } else {
@@ -355,13 +392,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                         gout[(int64_t)n * p.act_ld[l] + k] = zr[k];
                                         p.probs[(int64_t)(row0 + n) * p.ldp + k] = pr;
                                         if (p.dz[l] != nullptr) p.dz[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = dzv;
+                                        if (p.split && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
                                     }
-                                    if (p.do_bwd) *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, k, b_bytes)) = dzv;
+                                    if (p.do_bwd) st_tile(dst, n, k, dzv);
                                 }
                             }
                             if (p.do_bwd)                               // features [C, 32) of the k-block must be finite zeros
-                                for (int k = C; k < 32; ++k)
-                                    *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, k, b_bytes)) = 0.f;
+                                for (int k = C; k < 32; ++k) st_tile(dst, n, k, 0.f);
                         }
                         loss = warp_sum_f(loss);
                         if (lane == 0 && p.loss != nullptr) p.loss[p.mu_base + blockIdx.x] = loss * p.inv_batch;
@@ -386,8 +423,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     x = g[(int64_t)n * p.act_ld[L] + m];
                     if (ly.relu && !(y[(int64_t)n * p.act_ld[L] + m] > 0.f)) x = 0.f;
                     g[(int64_t)n * p.act_ld[L] + m] = x;     // the wgrad GEMM reads the masked gradient
+                    if (p.split) p.dz_lo[L][(int64_t)(row0 + n) * p.act_ld[L] + m] = tf32_lo(x);
                 }
-                *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, m, b_bytes)) = x;
+                st_tile(dst, n, m, x);
             }
             publish();
             wbuf ^= 1;
@@ -430,9 +468,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const int n = c + j;
                         float x = (mk[j] > 0.f) ? v[j] : 0.f;
                         x = m_ok ? x : 0.f;
-                        if (more) *reinterpret_cast<float*>(smem_gen + (dst - smem_base) + act_smem_off(n, m, b_bytes)) = x;
+                        if (more) st_tile(dst, n, m, x);
                         if (single) keep[j] = x;
-                        else if (m_ok && n < p.mb_rows) gprev[(int64_t)n * p.act_ld[l - 1] + m] = x;
+                        else if (m_ok && n < p.mb_rows) {
+                            gprev[(int64_t)n * p.act_ld[l - 1] + m] = x;
+                            if (p.split) p.dz_lo[l - 1][(int64_t)(row0 + n) * p.act_ld[l - 1] + m] = tf32_lo(x);
+                        }
                     }
                 }
                 if (more) {
@@ -442,7 +483,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 if (single && m_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c_lo + j < p.mb_rows) gprev[(int64_t)(c_lo + j) * p.act_ld[l - 1] + m] = keep[j];
+                        if (c_lo + j < p.mb_rows) {
+                            gprev[(int64_t)(c_lo + j) * p.act_ld[l - 1] + m] = keep[j];
+                            if (p.split) p.dz_lo[l - 1][(int64_t)(row0 + c_lo + j) * p.act_ld[l - 1] + m] = tf32_lo(keep[j]);
+                        }
                 }
             }
         }
@@ -469,22 +513,29 @@ bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out
     return true;
 }
 
-const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches) {
+const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
+                       const float* W_lo, const float* x_lo) {
     *plan = ChainPlan{};
     ChainParams& p = plan->p;
     p = params;
     const int L = p.n_layers;
     p.n_pad = (p.mb_rows + 15) / 16 * 16;
-    std::vector<CUtensorMap> host(2 * L + 1);
-    for (int l = 0; l < L; ++l) {
-        const ChainLayer& ly = p.layers[l];
-        if (const char* e = make_tmap_k(&host[2 * l], p.W + ly.w_off, ly.in, ly.out, ly.ldw, kBlockM)) return e;
-        if (const char* e = make_tmap_mn(&host[2 * l + 1], p.W + ly.w_off, ly.in, ly.out, ly.ldw)) return e;
-    }
-    if (x != nullptr) {
-        if (const char* e = make_tmap_k(&host[2 * L], x, p.layers[0].in, total_rows, ldx, p.n_pad)) return e;
-    } else {
-        host[2 * L] = host[0];
+    p.split = (W_lo != nullptr) ? 1 : 0;
+    const int nmaps = 2 * L + 1;
+    std::vector<CUtensorMap> host(nmaps * (p.split ? 2 : 1));
+    for (int half = 0; half < (p.split ? 2 : 1); ++half) {
+        const float* Wb = half ? W_lo : p.W;
+        const float* xb = half ? x_lo : x;
+        for (int l = 0; l < L; ++l) {
+            const ChainLayer& ly = p.layers[l];
+            if (const char* e = make_tmap_k(&host[half * nmaps + 2 * l], Wb + ly.w_off, ly.in, ly.out, ly.ldw, kBlockM)) return e;
+            if (const char* e = make_tmap_mn(&host[half * nmaps + 2 * l + 1], Wb + ly.w_off, ly.in, ly.out, ly.ldw)) return e;
+        }
+        if (xb != nullptr) {
+            if (const char* e = make_tmap_k(&host[half * nmaps + 2 * L], xb, p.layers[0].in, total_rows, ldx, p.n_pad)) return e;
+        } else {
+            host[half * nmaps + 2 * L] = host[half * nmaps];
+        }
     }
     CUtensorMap* dev = nullptr;
     if (cudaMalloc(&dev, host.size() * sizeof(CUtensorMap)) != cudaSuccess) return "chain_plan: cudaMalloc failed";
@@ -494,10 +545,10 @@ const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* 
     p.maps = dev;
     const int abuf_bytes = 4 * p.n_pad * 128;
     const int scratch_bytes = p.n_pad * kScratchLd * 4 + 256;
-    const int budget = 222 * 1024 - 2 * abuf_bytes - scratch_bytes;
+    const int budget = 222 * 1024 - (p.split ? 4 : 2) * abuf_bytes - scratch_bytes;
     int kps = 4, stage_bytes = 0, stages = 0;
     for (; kps >= 1; kps >>= 1) {            // biggest stage (fewest waits/commits) that still double-buffers
-        stage_bytes = kps * ((int)kABytes + p.n_pad * 128);
+        stage_bytes = kps * ((int)kABytes + p.n_pad * 128) * (p.split ? 2 : 1);
         stages = budget / stage_bytes;
         if (stages >= 2) break;
     }
@@ -505,7 +556,7 @@ const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* 
     if (stages > 8) stages = 8;
     p.kps = kps;
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + 2 * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
+    plan->smem_bytes = stages * stage_bytes + (p.split ? 4 : 2) * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
     plan->grid = n_mubatches;
     return nullptr;
 }

@@ -187,6 +187,15 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, uint
            | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ 3xTF32 operand splitting
+// tcgen05.mma.kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands (measured on
+// B200: 1+2^-11+2^-12 -> 1, 1+2^-10-2^-23 -> 1, sign-symmetric).  So the raw fp32 tile is the exact
+// "hi" operand trunc(x), and lo = x - trunc(x) (exact in fp32) is the only extra tensor needed for
+// an fp32-equivalent product  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (error ~2^-20 relative).
+__device__ __forceinline__ float tf32_lo(float x) {
+    return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
 // ------------------------------------------------------------------ system-scope flags (peer memory)
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -33,7 +33,8 @@ static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
     constexpr bool A_MN = (MODE != GEMM_FWD);
     constexpr bool B_MN = (MODE == GEMM_WGRAD);
 
@@ -47,7 +48,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.y * p.block_n;
     const int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
     const uint32_t b_bytes = p.block_n * 128u;
-    const uint32_t stage_bytes = kABytes + b_bytes;
+    const uint32_t half_bytes = kABytes + b_bytes;              // [A][B]; split mode appends [A_lo][B_lo]
+    const uint32_t stage_bytes = p.split ? 2u * half_bytes : half_bytes;
     // WGRAD stages its output tile (block_n/32 swizzled panels of [128 rows x 128 B]) behind the ring
     const uint32_t epi_base = smem_base + p.stages * stage_bytes;
     const uint32_t epi_bytes = (MODE == GEMM_WGRAD) ? (uint32_t)p.block_n * 512u : 0u;
@@ -108,6 +110,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < p.block_n / 32; ++j)
                         tma_load_2d(b_dst + j * kPanelBytes, &tmB, full_bar(s), n0 + 32 * j, k0);
                 }
+                if (p.split) {                                // lo twins: same boxes, second half of the stage
+                    const uint32_t al = a_dst + half_bytes, bl = b_dst + half_bytes;
+                    if (!A_MN) {
+                        tma_load_2d(al, &tmAlo, full_bar(s), k0, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tma_load_2d(al + i * kPanelBytes, &tmAlo, full_bar(s), m0 + 32 * i, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(bl, &tmBlo, full_bar(s), k0, n0);
+                    } else {
+                        for (int j = 0; j < p.block_n / 32; ++j)
+                            tma_load_2d(bl + j * kPanelBytes, &tmBlo, full_bar(s), n0 + 32 * j, k0);
+                    }
+                }
             }
             __syncwarp();
         }
@@ -130,6 +147,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 constexpr uint32_t a_step = A_MN ? (1024u >> 4) : (32u >> 4);
                 constexpr uint32_t b_step = B_MN ? (1024u >> 4) : (32u >> 4);
                 if (elect_one()) {
+                    if (p.split) {
+                        // fp32-equivalent product: small terms first, then hi*hi (the raw tiles ARE the hi parts)
+                        const uint32_t al_lo = a_lo + (half_bytes >> 4), bl_lo = b_lo + (half_bytes >> 4);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            umma_tf32(tmem_base, umma_desc_pack(al_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
+                                      idesc, (kb | k4) != 0 ? 1u : 0u);
+                            umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
+                                      idesc, 1u);
+                            umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
+                                      idesc, 1u);
+                        }
+                    } else
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
                         umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi), idesc,
@@ -202,7 +232,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n = n0 + c + j;
-                    if (n < p.n_total) out[(size_t)n * p.ldo + m] = v[j];     // lanes -> consecutive m: coalesced
+                    if (n < p.n_total) {
+                        out[(size_t)n * p.ldo + m] = v[j];     // lanes -> consecutive m: coalesced
+                        if (p.out_lo != nullptr) p.out_lo[(size_t)n * p.ldo + m] = tf32_lo(v[j]);
+                    }
                 }
             }
         } else {
@@ -320,7 +353,7 @@ static int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 static void finish_plan(GemmPlan* plan) {
     GemmParams& p = plan->p;
     const int num_kb = (p.k_total + (int)kBlockK - 1) / (int)kBlockK;
-    const int stage_bytes = (int)kABytes + p.block_n * 128;
+    const int stage_bytes = ((int)kABytes + p.block_n * 128) * (p.split ? 2 : 1);
     const int epi_bytes = plan->mode == GEMM_WGRAD ? p.block_n * 512 : 0;
     int stages = (200 * 1024 - epi_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
@@ -332,7 +365,7 @@ static void finish_plan(GemmPlan* plan) {
 }
 
 const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* X, int ldx, float* Y, int ldy, int rows,
-                          int in, int out, const float* bias, int bias_stride, int relu) {
+                          int in, int out, const float* bias, int bias_stride, int relu, GemmLo lo) {
     *plan = GemmPlan{};
     plan->mode = GEMM_FWD;
     GemmParams& p = plan->p;
@@ -342,12 +375,18 @@ const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* 
     if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, kBlockM)) return e;
     if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, p.block_n)) return e;
     plan->tmC = plan->tmA;
+    plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
+    if (lo.A != nullptr && lo.B != nullptr) {
+        p.split = 1; p.out_lo = lo.out;
+        if (const char* e = make_tmap(&plan->tmAlo, lo.A, in, out, ldw, kBlockM)) return e;
+        if (const char* e = make_tmap(&plan->tmBlo, lo.B, in, rows, ldx, p.block_n)) return e;
+    }
     finish_plan(plan);
     return nullptr;
 }
 
 const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float* dZ, int lddz, float* dX, int lddx,
-                            int rows, int in, int out, const float* mask, int ldmask) {
+                            int rows, int in, int out, const float* mask, int ldmask, GemmLo lo) {
     *plan = GemmPlan{};
     plan->mode = GEMM_DGRAD;
     GemmParams& p = plan->p;
@@ -357,13 +396,19 @@ const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float
     if (const char* e = make_tmap(&plan->tmA, W, in, out, ldw, 32, true)) return e;          // MN-major panels [32 k x 32 m]
     if (const char* e = make_tmap(&plan->tmB, dZ, out, rows, lddz, p.block_n)) return e;
     plan->tmC = plan->tmA;
+    plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
+    if (lo.A != nullptr && lo.B != nullptr) {
+        p.split = 1; p.out_lo = lo.out;
+        if (const char* e = make_tmap(&plan->tmAlo, lo.A, in, out, ldw, 32, true)) return e;
+        if (const char* e = make_tmap(&plan->tmBlo, lo.B, out, rows, lddz, p.block_n)) return e;
+    }
     finish_plan(plan);
     return nullptr;
 }
 
 const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const float* X, int ldx, float* G, int ldg,
                             int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
-                            float lr, int fuse_sgd) {
+                            float lr, int fuse_sgd, GemmLo lo) {
     *plan = GemmPlan{};
     plan->mode = GEMM_WGRAD;
     GemmParams& p = plan->p;
@@ -377,6 +422,12 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
     if (const char* e = make_tmap(&plan->tmC, fuse_sgd ? W : G, in, out, fuse_sgd ? ldw : ldg, kBlockM)) return e;
     if (const char* e = make_tmap(&plan->tmA, dZ, out, rows, lddz, 32, true)) return e;
     if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, 32, true)) return e;
+    plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
+    if (lo.A != nullptr && lo.B != nullptr) {
+        p.split = 1;
+        if (const char* e = make_tmap(&plan->tmAlo, lo.A, out, rows, lddz, 32, true)) return e;
+        if (const char* e = make_tmap(&plan->tmBlo, lo.B, in, rows, ldx, 32, true)) return e;
+    }
     finish_plan(plan);
     return nullptr;
 }
@@ -403,7 +454,7 @@ static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
         cudaError_t e = gemm_configure();
         if (e != cudaSuccess) return e;
     }
-    tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
+    tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

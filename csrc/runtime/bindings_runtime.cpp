@@ -102,6 +102,7 @@ public:
         c.training = geti("training", 1); c.use_graph = geti("use_graph", 1);
         c.dp_size = geti("dp_size", 1); c.dp_rank = geti("dp_rank", 0); c.dp_mode = geti("dp_mode", 0);
         c.in_dim = geti("in_dim", 784); c.out_dim = geti("out_dim", 10);
+        c.split = geti("split", 0);
         c10::cuda::CUDAGuard guard(weights.device());
         engine_ = std::make_unique<PipeEngine>(c, weights.data_ptr<float>(), grads.data_ptr<float>(), weights.numel());
     }
@@ -149,6 +150,8 @@ public:
     }
     int64_t kernels_per_step() { return engine_->kernels_per_step(); }
     int64_t graph_nodes() { return engine_->graph_nodes(); }
+    bool uses_chain() { return engine_->uses_chain(); }
+    bool coalesced() { return engine_->coalesced(); }
     int64_t main_stream() { return reinterpret_cast<int64_t>(engine_->main_stream()); }
     std::string describe() { return engine_->describe(); }
     std::vector<unsigned long long> chain_timeline() { return engine_->chain_timeline(); }
@@ -191,6 +194,8 @@ void bind_runtime(py::module_& m) {
         .def("probs", &PyEngine::probs)
         .def("kernels_per_step", &PyEngine::kernels_per_step)
         .def("graph_nodes", &PyEngine::graph_nodes)
+        .def("uses_chain", &PyEngine::uses_chain)
+        .def("coalesced", &PyEngine::coalesced)
         .def("main_stream", &PyEngine::main_stream)
         .def("describe", &PyEngine::describe)
         .def("chain_timeline", &PyEngine::chain_timeline);

@@ -107,6 +107,23 @@ void PipeEngine::alloc_buffers() {
     if (cfg_.training)
         for (int l = 0; l <= L_; ++l) dz_all_[l] = dalloc((size_t)M * mb * act_ld_[l]);
     probs_all_ = dalloc((size_t)M * mb * act_ld_[L_]);
+    act_lo_all_.assign(L_ + 1, nullptr);
+    dz_lo_all_.assign(L_ + 1, nullptr);
+    act_lo_.assign(M, std::vector<float*>(L_ + 1, nullptr));
+    dz_lo_.assign(M, std::vector<float*>(L_ + 1, nullptr));
+    if (cfg_.split) {
+        W_lo_ = dalloc((size_t)arena_numel_);
+        for (int set = 0; set < 2; ++set) x_lo_sets_[set] = dalloc((size_t)M * mb * act_ld_[0]);
+        act_lo_all_[0] = x_lo_sets_[0];
+        for (int l = 1; l <= L_; ++l) act_lo_all_[l] = dalloc((size_t)M * mb * act_ld_[l]);
+        if (cfg_.training)
+            for (int l = 0; l <= L_; ++l) dz_lo_all_[l] = dalloc((size_t)M * mb * act_ld_[l]);
+        for (int mu = 0; mu < M; ++mu)
+            for (int l = 0; l <= L_; ++l) {
+                act_lo_[mu][l] = act_lo_all_[l] + (size_t)mu * mb * act_ld_[l];
+                if (cfg_.training) dz_lo_[mu][l] = dz_lo_all_[l] + (size_t)mu * mb * act_ld_[l];
+            }
+    }
     act_.assign(M, std::vector<float*>(L_ + 1, nullptr));
     dz_.assign(M, std::vector<float*>(L_ + 1, nullptr));
     probs_.assign(M, nullptr);
@@ -126,6 +143,35 @@ void PipeEngine::select_set(int set) {
     y_stage_ = y_stage_sets_[set];
     act_all_[0] = x_stage_;
     for (int mu = 0; mu < cfg_.n_mu; ++mu) act_[mu][0] = act_all_[0] + (size_t)mu * cfg_.mb_rows * act_ld_[0];
+    if (cfg_.split) {
+        act_lo_all_[0] = x_lo_sets_[set];
+        for (int mu = 0; mu < cfg_.n_mu; ++mu) act_lo_[mu][0] = act_lo_all_[0] + (size_t)mu * cfg_.mb_rows * act_ld_[0];
+    }
+}
+
+// lo-twin operand sets for the three GEMMs of layer l (mu < 0: all micro-batches at once)
+GemmLo PipeEngine::lo_fwd(int l, int mu) const {
+    GemmLo g;
+    if (!cfg_.split) return g;
+    g.A = W_lo_ + cfg_.layers[l - 1].offset;
+    g.B = mu < 0 ? act_lo_all_[l - 1] : act_lo_[mu][l - 1];
+    g.out = mu < 0 ? act_lo_all_[l] : act_lo_[mu][l];
+    return g;
+}
+GemmLo PipeEngine::lo_dgrad(int l, int mu) const {
+    GemmLo g;
+    if (!cfg_.split) return g;
+    g.A = W_lo_ + cfg_.layers[l - 1].offset;
+    g.B = mu < 0 ? dz_lo_all_[l] : dz_lo_[mu][l];
+    g.out = mu < 0 ? dz_lo_all_[l - 1] : dz_lo_[mu][l - 1];
+    return g;
+}
+GemmLo PipeEngine::lo_wgrad(int l, int mu) const {
+    GemmLo g;
+    if (!cfg_.split) return g;
+    g.A = mu < 0 ? dz_lo_all_[l] : dz_lo_[mu][l];
+    g.B = mu < 0 ? act_lo_all_[l - 1] : act_lo_[mu][l - 1];
+    return g;
 }
 
 int PipeEngine::new_event() {
@@ -161,6 +207,8 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
         cp.act[l] = act_all_[l];
         cp.dz[l] = cfg_.training ? dz_all_[l] : nullptr;
         cp.act_ld[l] = act_ld_[l];
+        cp.act_lo[l] = cfg_.split ? act_lo_all_[l] : nullptr;
+        cp.dz_lo[l] = (cfg_.split && cfg_.training) ? dz_lo_all_[l] : nullptr;
     }
     cp.target = y_stage_; cp.ldt = y_ld_;
     cp.probs = probs_all_; cp.ldp = act_ld_[L_];
@@ -179,7 +227,8 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
         cp.dbg = chain_dbg_;
     }
     ChainPlan plan;
-    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu);
+    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, cfg_.split ? W_lo_ : nullptr,
+                                 cfg_.split ? act_lo_all_[0] : nullptr);
     if (err) throw std::runtime_error(std::string("PipeEngine chain plan: ") + err);
     chain_plans_.push_back(plan);
     Op op;
@@ -252,6 +301,11 @@ void PipeEngine::plan_per_mubatch() {
     const bool first = cfg_.is_first, last = cfg_.is_last;
     std::vector<bool> started(streams_.size(), false);
     started[0] = true;
+    if (cfg_.split && !cfg_.training) {      // inference: weights are updated by the training engine between calls
+        Op sp;
+        sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
+        ops_.push_back(sp);
+    }
     Op begin;
     begin.kind = OP_RECORD; begin.stream = 0; begin.event = new_event();
     ops_.push_back(begin);
@@ -331,7 +385,15 @@ void PipeEngine::plan_per_mubatch() {
             case I_FORWARD: {
                 const int s = sm(mu);
                 use(s);
-                if (ev_in[mu] >= 0) { emit_wait(s, ev_in[mu]); ev_in[mu] = -1; }
+                if (ev_in[mu] >= 0) {
+                    emit_wait(s, ev_in[mu]);
+                    ev_in[mu] = -1;
+                    if (cfg_.split) {   // activations arrived over NCCL: build their lo twin before the first GEMM reads it
+                        Op sp;
+                        sp.kind = OP_SPLIT; sp.stream = s; sp.a = act_[mu][0]; sp.b = act_lo_[mu][0]; sp.n = (int64_t)mb * act_ld_[0];
+                        ops_.push_back(sp);
+                    }
+                }
                 if (chain_ok_) {
                     // whole stage forward (+ loss head on the last stage) of this micro-batch in one launch
                     add_chain(s, mu, 1, true, last, false);
@@ -347,7 +409,7 @@ void PipeEngine::plan_per_mubatch() {
                         const LayerSpec& ls = cfg_.layers[l - 1];
                         GemmPlan g;
                         check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_[mu][l - 1], act_ld_[l - 1], act_[mu][l], act_ld_[l], mb,
-                                            ls.in, ls.out, Wl(l) + ls.in, ls.ld, ls.relu));
+                                            ls.in, ls.out, Wl(l) + ls.in, ls.ld, ls.relu, lo_fwd(l, mu)));
                         add_gemm(g, s, l, mu);
                     }
                     if (!cfg_.training && last) {
@@ -384,7 +446,8 @@ void PipeEngine::plan_per_mubatch() {
                         emit_wait(w, ev_dz_all);
                         GemmPlan g;
                         check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
-                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0,
+                                              lo_wgrad(l, mu)));
                         add_gemm(g, w, l, mu);
                         first_write[l] = false;
                         if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
@@ -406,12 +469,14 @@ void PipeEngine::plan_per_mubatch() {
                         lh.c = probs_[mu]; lh.ldc = act_ld_[L_];
                         lh.d = dz_[mu][L_]; lh.ldd = act_ld_[L_];
                         lh.rows = mb; lh.cols = cfg_.out_dim; lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = mu;
+                    lh.e = cfg_.split ? dz_lo_[mu][L_] : nullptr;
                         ops_.push_back(lh);
                     } else if (L_ > 0 && cfg_.layers[L_ - 1].relu) {
                         Op rm;
                         rm.kind = OP_RELU_MASK; rm.stream = s;
                         rm.a = dz_[mu][L_]; rm.lda = act_ld_[L_]; rm.b = act_[mu][L_]; rm.ldb = act_ld_[L_];
                         rm.rows = mb; rm.cols = cfg_.layers[L_ - 1].out;
+                    rm.e = cfg_.split ? dz_lo_[mu][L_] : nullptr;
                         ops_.push_back(rm);
                     }
                     for (int l = L_; l >= 1; --l) {
@@ -422,7 +487,8 @@ void PipeEngine::plan_per_mubatch() {
                         emit_wait(w, ev_dz);
                         GemmPlan g;
                         check(gemm_plan_wgrad(&g, dz_[mu][l], act_ld_[l], act_[mu][l - 1], act_ld_[l - 1], Gl(l), ls.ld, mb,
-                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0));
+                                              ls.in, ls.out, first_write[l] ? 0 : 1, Gl(l) + ls.in, ls.ld, nullptr, 0, 0.f, 0,
+                                              lo_wgrad(l, mu)));
                         add_gemm(g, w, l, mu);
                         first_write[l] = false;
                         if (final_bwd && cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
@@ -438,7 +504,7 @@ void PipeEngine::plan_per_mubatch() {
                             const float* mask = (l >= 2 && cfg_.layers[l - 2].relu) ? act_[mu][l - 1] : nullptr;
                             GemmPlan g2;
                             check(gemm_plan_dgrad(&g2, Wl(l), ls.ld, dz_[mu][l], act_ld_[l], dz_[mu][l - 1], act_ld_[l - 1], mb, ls.in,
-                                                  ls.out, mask, act_ld_[l - 1]));
+                                                  ls.out, mask, act_ld_[l - 1], lo_dgrad(l, mu)));
                             add_gemm(g2, s, l, mu);
                         }
                     }
@@ -491,6 +557,11 @@ void PipeEngine::plan_per_mubatch() {
     // ---- join every side stream back into the main stream
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
+    if (cfg_.split && cfg_.training) {       // weights changed: refresh their lo twin for the next step
+        Op sp;
+        sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
+        ops_.push_back(sp);
+    }
     if (cfg_.training && last) {
         Op cp;
         cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
@@ -524,6 +595,11 @@ void PipeEngine::build_coalesced() {
     auto use = [&](int s) { if (!started[s]) { emit_wait(s, ev_begin); started[s] = true; } };
     auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
 
+    if (cfg_.split && !cfg_.training) {      // weights are updated by the training engine between calls
+        Op sp;
+        sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
+        ops_.push_back(sp);
+    }
     const bool chain = chain_ok_;
     if (chain) {
         // forward + loss head (+ whole dgrad chain when training) of every micro-batch in ONE launch
@@ -540,7 +616,7 @@ void PipeEngine::build_coalesced() {
             const LayerSpec& ls = cfg_.layers[l - 1];
             GemmPlan g;
             check(gemm_plan_fwd(&g, Wl(l), ls.ld, act_all_[l - 1], act_ld_[l - 1], act_all_[l], act_ld_[l], rows, ls.in, ls.out,
-                                Wl(l) + ls.in, ls.ld, ls.relu));
+                                Wl(l) + ls.in, ls.ld, ls.relu, lo_fwd(l, -1)));
             add_gemm(g, 0, l);
         }
         if (!cfg_.training) {
@@ -560,6 +636,7 @@ void PipeEngine::build_coalesced() {
         lh.a = act_all_[L_]; lh.lda = act_ld_[L_]; lh.b = y_stage_; lh.ldb = y_ld_; lh.c = probs_all_; lh.ldc = act_ld_[L_];
         lh.d = dz_all_[L_]; lh.ldd = act_ld_[L_]; lh.rows = rows; lh.cols = cfg_.out_dim;
         lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = 0; lh.n = mb;
+        lh.e = cfg_.split ? dz_lo_all_[L_] : nullptr;
         ops_.push_back(lh);
     }
     const bool fuse = (cfg_.dp_mode == 0);
@@ -582,7 +659,7 @@ void PipeEngine::build_coalesced() {
             const float* mask = cfg_.layers[l - 2].relu ? act_all_[l - 1] : nullptr;
             GemmPlan g;
             check(gemm_plan_dgrad(&g, Wl(l), ls.ld, dz_all_[l], act_ld_[l], dz_all_[l - 1], act_ld_[l - 1], rows, ls.in, ls.out,
-                                  mask, act_ld_[l - 1]));
+                                  mask, act_ld_[l - 1], lo_dgrad(l, -1)));
             add_gemm(g, 0, l);
             ev_dg = emit_record(0);
         }
@@ -605,7 +682,8 @@ void PipeEngine::build_coalesced() {
                 }
                 lp.dbg = chain_dbg_ + 3 * 256 + 8 * l;
             }
-            check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, lp, dp_ctx_->peers(), kFusedDpMaxCtas));
+            check(fused_dp_plan(&fp, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], rows, lp, dp_ctx_->peers(), kFusedDpMaxCtas,
+                                cfg_.split ? dz_lo_all_[l] : nullptr, cfg_.split ? act_lo_all_[l - 1] : nullptr));
             dp_plans_.push_back(fp);
             Op fo;
             fo.kind = OP_FUSED_DP; fo.stream = sdp; fo.gemm = (int)dp_plans_.size() - 1; fo.layer = l;
@@ -618,7 +696,7 @@ void PipeEngine::build_coalesced() {
         if (fuse && ev_dg >= 0) emit_wait(w, ev_dg);      // W_l is updated in place: its last reader must be done
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
-                              Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0));
+                              Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
         add_gemm(g, w, l);
         if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
             const int ev_g = emit_record(w);
@@ -643,6 +721,11 @@ void PipeEngine::build_coalesced() {
     }
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
+    if (cfg_.split) {                        // weights changed: refresh their lo twin for the next step
+        Op sp;
+        sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
+        ops_.push_back(sp);
+    }
     Op cp;
     cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
     ops_.push_back(cp);
@@ -653,7 +736,7 @@ void PipeEngine::finish_build() {
     for (auto& op : ops_sets_[0]) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
-            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN)
+            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -661,6 +744,11 @@ void PipeEngine::finish_build() {
     // kernel attributes are configured up front (never inside a capture); communicators are
     // warmed up by their creator.  No eager pass here: a training step mutates the weights.
     CUDA_CHECK(gemm_configure());
+    if (cfg_.split) {                        // first step needs a valid lo twin of the initial weights
+        CUDA_CHECK(launch_split_lo(W_, W_lo_, arena_numel_, streams_[0]));
+        CUDA_CHECK(cudaStreamSynchronize(streams_[0]));
+        ++kernels_per_step_;                 // + the staged-input split issued on the copy stream every step
+    }
     if (!chain_plans_.empty()) CUDA_CHECK(chain_configure());
     if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
     if (cfg_.use_graph) {
@@ -684,7 +772,7 @@ void PipeEngine::exec(const Op& op) {
         case OP_GEMM: CUDA_CHECK(gemm_launch(gemms_[op.gemm], st)); break;
         case OP_LOSS_HEAD:
             CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, loss_dev_ + op.mu, op.rows,
-                                        op.cols, op.scalar, st, (int)op.n));
+                                        op.cols, op.scalar, st, (int)op.n, op.e));
             break;
         case OP_SOFTMAX:
             CUDA_CHECK(launch_loss_head(op.a, op.lda, nullptr, 0, op.b, op.ldb, nullptr, 0, nullptr, op.rows, op.cols, 0.f, st,
@@ -693,7 +781,8 @@ void PipeEngine::exec(const Op& op) {
         case OP_ARGMAX:
             CUDA_CHECK(launch_argmax_correct(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, correct_dev_, st));
             break;
-        case OP_RELU_MASK: CUDA_CHECK(launch_relu_mask(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, st)); break;
+        case OP_RELU_MASK: CUDA_CHECK(launch_relu_mask(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, st, op.e)); break;
+        case OP_SPLIT: CUDA_CHECK(launch_split_lo(op.a, op.b, (long)op.n, st)); break;
         case OP_SGD: CUDA_CHECK(launch_sgd(op.a, op.b, op.scalar, op.n, st)); break;
         case OP_ALLREDUCE:
             if (!dp_comm_) throw std::runtime_error("PipeEngine: DP all-reduce without a communicator");
@@ -738,6 +827,8 @@ void PipeEngine::stage_inputs(const float* x, const float* y, bool from_host) {
     if (y != nullptr && cfg_.is_last)
         CUDA_CHECK(cudaMemcpy2DAsync(y_stage_sets_[set], (size_t)y_ld_ * 4, y, (size_t)cfg_.out_dim * 4, (size_t)cfg_.out_dim * 4,
                                      rows, kind, copy_stream_));
+    if (cfg_.split && x != nullptr && cfg_.is_first)   // lo twin of the staged inputs, off the critical path
+        CUDA_CHECK(launch_split_lo(x_stage_sets_[set], x_lo_sets_[set], (long)rows * act_ld_[0], copy_stream_));
     CUDA_CHECK(cudaEventRecord(ev_copy_[set], copy_stream_));
     staged_ = true;
 }

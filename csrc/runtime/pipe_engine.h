@@ -40,7 +40,7 @@ struct LayerSpec {
 
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
-    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN
+    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -58,7 +58,7 @@ struct Op {
     int layer = -1, mu = -1;
     std::vector<CommItem> comm;
     // generic pointers for the small kernels
-    float *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+    float *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr, *e = nullptr;   // e: lo twin of the output (split mode)
     int lda = 0, ldb = 0, ldc = 0, ldd = 0, rows = 0, cols = 0;
     float scalar = 0.f;
     int64_t n = 0;
@@ -77,6 +77,7 @@ struct EngineConfig {
     int dp_size = 1, dp_rank = 0;
     int dp_mode = 0;        // 0 = none/fused-sgd (dp=1), 1 = NCCL all-reduce + SGD, 2 = fused in-kernel reduction
     int in_dim = 784, out_dim = 10;
+    int split = 0;          // 1 = fp32-equivalent tensor-core products (3xTF32), 0 = single-pass TF32
 };
 
 class PipeEngine {
@@ -139,6 +140,13 @@ private:
     std::vector<std::vector<float*>> act_, dz_;  // [mu][l]
     std::vector<float*> probs_;
     std::vector<float*> act_all_, dz_all_;       // [l] contiguous over micro-batches
+    std::vector<float*> act_lo_all_, dz_lo_all_; // lo twins (split mode)
+    std::vector<std::vector<float*>> act_lo_, dz_lo_;
+    float* W_lo_ = nullptr;
+    float* x_lo_sets_[2] = {nullptr, nullptr};
+    GemmLo lo_fwd(int l, int mu) const;
+    GemmLo lo_dgrad(int l, int mu) const;
+    GemmLo lo_wgrad(int l, int mu) const;
     float* probs_all_ = nullptr;
     bool coalesced_ = false;
     float *x_stage_ = nullptr, *y_stage_ = nullptr, *loss_dev_ = nullptr, *loss_host_ = nullptr;

@@ -57,27 +57,55 @@ def _bias_arg(bias, out_dims):
 
 
 # ------------------------------------------------------------------ GEMMs
-def linear_fwd(x, weight, bias=None, relu=False, out=None):
+# precision: "tf32" = one tcgen05.mma.kind::tf32 pass (operands truncated to 10 mantissa bits);
+#            "fp32" = 3xTF32: lo twins (x - trunc(x)) of both operands, three MMAs per k-slice, error ~2^-20.
+PRECISION = "fp32"
+
+
+def _split(precision):
+    return (precision or PRECISION) in ("fp32", "fp32x3", "3xtf32")
+
+
+def lo_twin(t: torch.Tensor) -> torch.Tensor:
+    """lo = t - trunc_tf32(t), same padded layout as t (t must be tma_ready)."""
+    base = torch.zeros(t.size(0), t.stride(0), dtype=torch.float32, device=t.device)
+    lo = base[:, : t.size(1)]
+    assert lo.stride(0) == t.stride(0)
+    _C.split_lo(t, lo)
+    return lo
+
+
+def linear_fwd(x, weight, bias=None, relu=False, out=None, precision=None):
     x, weight = as_tma(x), as_tma(weight)
     rows, out_dims = x.size(0), weight.size(0)
     y = out if out is not None else empty_padded(rows, out_dims, x.device)
     b, bstride = _bias_arg(bias, out_dims)
-    _C.linear_fwd(x, weight, b, bstride, bool(relu), y)
+    if _split(precision):
+        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, lo_twin(weight), lo_twin(x), None)
+    else:
+        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, None, None, None)
     return y
 
 
-def linear_dgrad(dz, weight, mask=None, out=None):
+def linear_dgrad(dz, weight, mask=None, out=None, precision=None):
     dz, weight = as_tma(dz), as_tma(weight)
     dx = out if out is not None else empty_padded(dz.size(0), weight.size(1), dz.device)
-    _C.linear_dgrad(dz, weight, None if mask is None else as_tma(mask), dx)
+    m = None if mask is None else as_tma(mask)
+    if _split(precision):
+        _C.linear_dgrad(dz, weight, m, dx, lo_twin(weight), lo_twin(dz), None)
+    else:
+        _C.linear_dgrad(dz, weight, m, dx, None, None, None)
     return dx
 
 
-def linear_wgrad(dz, x, grad_w, accumulate=False, grad_b=None, weight=None, lr=0.0, fuse_sgd=False):
+def linear_wgrad(dz, x, grad_w, accumulate=False, grad_b=None, weight=None, lr=0.0, fuse_sgd=False, precision=None):
     """grad_w[out, in] (+)= dz^T @ x ; grad_b (+)= colsum(dz)."""
     dz, x = as_tma(dz), as_tma(x)
     b, bstride = _bias_arg(grad_b, dz.size(1))
-    _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd))
+    if _split(precision):
+        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), lo_twin(dz), lo_twin(x))
+    else:
+        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), None, None)
     return grad_w
 
 

@@ -63,7 +63,7 @@ def make_nccl_comm(comm: Comm):
 
 class NativeWorker:
     def __init__(self, dp_comm, pp_comm, model, dataset, optimizer, grid: Optional[ProcessGrid] = None,
-                 comm_mode: str = "fused", use_graph: bool = True, precision: str = "tf32", share=None,
+                 comm_mode: str = "fused", use_graph: bool = True, precision: str = "fp32", share=None,
                  validate_schedules: bool = True):
         self.dp_comm = dp_comm if dp_comm is not None else SelfComm()
         self.pp_comm = pp_comm if pp_comm is not None else SelfComm()
@@ -112,7 +112,8 @@ class NativeWorker:
                    n_stages=sched.num_stages, mb_rows=self.dataset.mubatch_size, n_mu=sched.num_micro_batches,
                    global_batch=m.batch_size, lr=float(self.lr), training=int(training), use_graph=int(self.use_graph),
                    dp_size=self.dp_comm.Get_size(), dp_rank=self.dp_comm.Get_rank(),
-                   dp_mode=DP_MODE[self.dp_mode] if training else 0, in_dim=m.in_dim, out_dim=m.out_dim)
+                   dp_mode=DP_MODE[self.dp_mode] if training else 0, in_dim=m.in_dim, out_dim=m.out_dim,
+                   split=1 if self.precision in ("fp32", "fp32x3", "3xtf32") else 0)
         eng = _C().PipeEngine(specs, cfg, m.arena.weights, m.arena.grads)
         if self._pp_nccl is not None:
             eng.set_pp_comm(self._pp_nccl)
@@ -188,7 +189,7 @@ class Trainer:
 
     def __init__(self, layer_sizes, global_batch_size=128, n_mubatches=4, lr=0.006, schedule="naive",
                  dp_comm=None, pp_comm=None, grid: Optional[ProcessGrid] = None, comm_mode="fused",
-                 use_graph=True, device=None, seed_mode="shape"):
+                 use_graph=True, device=None, seed_mode="shape", precision="fp32"):
         from ..models.mlp import MLP
         from ..optimizer import SGD
         from .schedules import SCHEDULE_NAME_TO_CLS
@@ -206,7 +207,7 @@ class Trainer:
             mubatch_size = self.local_batch_size // n_mubatches
 
         self.worker = NativeWorker(dp_comm, pp_comm, self.model, _Shape(), self.optimizer, grid=grid,
-                                   comm_mode=comm_mode, use_graph=use_graph)
+                                   comm_mode=comm_mode, use_graph=use_graph, precision=precision)
         cls = SCHEDULE_NAME_TO_CLS[schedule] if isinstance(schedule, str) else schedule
         self.schedule = cls(n_mubatches, pp, self.pp_comm.Get_rank())
         self.engine = self.worker.engine_for(self.schedule)

@@ -23,39 +23,45 @@ SHAPES = [  # rows, in, out
 ]
 
 
+TOL = {"tf32": 3e-3, "fp32": 2e-5}     # single-pass TF32 (truncated operands) vs 3xTF32 (fp32-equivalent)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
 @pytest.mark.parametrize("rows,k,n", SHAPES)
 @pytest.mark.parametrize("relu", [False, True])
-def test_linear_fwd(rows, k, n, relu):
+def test_linear_fwd(rows, k, n, relu, precision):
     K = _K()
     torch.manual_seed(rows * 7 + k + n)
     x = torch.randn(rows, k, device="cuda")
     W = torch.randn(n, k, device="cuda") / k ** 0.5
     b = torch.randn(1, n, device="cuda")
-    y = K.linear_fwd(x, W, b, relu=relu)
+    y = K.linear_fwd(x, W, b, relu=relu, precision=precision)
     ref = x.double() @ W.double().T + b.double()
     if relu:
         ref = ref.clamp_min(0)
     assert y.shape == (rows, n)
-    assert rel_err(y.double(), ref) < 3e-3
+    assert rel_err(y.double(), ref) < TOL[precision]
 
 
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
 @pytest.mark.parametrize("rows,k,n", SHAPES)
-def test_linear_dgrad(rows, k, n):
+def test_linear_dgrad(rows, k, n, precision):
     K = _K()
     torch.manual_seed(rows + k * 3 + n)
     dz = torch.randn(rows, n, device="cuda")
     W = torch.randn(n, k, device="cuda") / n ** 0.5
     mask = torch.randn(rows, k, device="cuda")
-    dx = K.linear_dgrad(dz, W)
+    dx = K.linear_dgrad(dz, W, precision=precision)
     ref = dz.double() @ W.double()
-    assert rel_err(dx.double(), ref) < 3e-3
-    dxm = K.linear_dgrad(dz, W, mask=mask)
-    assert rel_err(dxm.double(), ref * (mask > 0)) < 3e-3
+    assert rel_err(dx.double(), ref) < TOL[precision]
+    dxm = K.linear_dgrad(dz, W, mask=mask, precision=precision)
+    assert rel_err(dxm.double(), ref * (mask > 0)) < TOL[precision]
 
 
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
 @pytest.mark.parametrize("rows,k,n", SHAPES)
 @pytest.mark.parametrize("accumulate", [False, True])
-def test_linear_wgrad(rows, k, n, accumulate):
+def test_linear_wgrad(rows, k, n, accumulate, precision):
     K = _K()
     torch.manual_seed(rows + k + n * 5)
     dz = torch.randn(rows, n, device="cuda")
@@ -63,13 +69,13 @@ def test_linear_wgrad(rows, k, n, accumulate):
     ld = (k + 1 + 7) // 8 * 8
     G = torch.randn(n, ld, device="cuda")
     G0 = G.clone()
-    K.linear_wgrad(dz, x, G[:, :k], accumulate=accumulate, grad_b=G[:, k])
+    K.linear_wgrad(dz, x, G[:, :k], accumulate=accumulate, grad_b=G[:, k], precision=precision)
     ref_w = dz.double().T @ x.double()
     ref_b = dz.double().sum(0)
     if accumulate:
         ref_w = ref_w + G0[:, :k].double()
         ref_b = ref_b + G0[:, k].double()
-    assert rel_err(G[:, :k].double(), ref_w) < 3e-3
+    assert rel_err(G[:, :k].double(), ref_w) < TOL[precision]
     assert rel_err(G[:, k].double(), ref_b) < 1e-5      # db is an exact fp32 reduction
     pad, pad0 = G[:, k + 1:], G0[:, k + 1:]              # padding: untouched, or zeroed by the 16-byte-granular TMA store
     assert bool(((pad == pad0) | (pad == 0)).all())
@@ -141,9 +147,9 @@ def test_module_path_matches_cpu():
     cpu, gpu = MLP(sizes, 0, 1, 128), MLP(sizes, 0, 1, 128).to("cuda")
     out_c = cpu.forward(x, 0)
     out_g = gpu.forward(x.cuda(), 0)
-    assert rel_err(out_g.cpu(), out_c) < 5e-3
+    assert rel_err(out_g.cpu(), out_c) < 5e-5
     cpu.backward(t, 0)
     gpu.backward(t.cuda(), 0)
     for pc, pg in zip(cpu.parameters(), gpu.parameters()):
-        # TF32 products through 14 chained GEMMs + ReLU sign flips near zero: compare in norm
-        assert float((pg.grad.cpu() - pc.grad).norm() / pc.grad.norm()) < 6e-2
+        # default precision is fp32 (3xTF32): 14 chained GEMMs agree with the CPU oracle to ~1e-5 in norm
+        assert float((pg.grad.cpu() - pc.grad).norm() / pc.grad.norm()) < 2e-4

@@ -9,10 +9,12 @@ import torch
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
+WIDE = [784, 1024, 1000, 1024, 520, 1024, 130, 10]     # > 128 wide: per-layer GEMM kernels, two-shot DP for the 4 MB layers
 GBS, N_MU, LR, STEPS = 128, 4, 0.05, 4
 
 
-def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce, two_shot=False):
+def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce, two_shot=False, sizes=None):
+    sizes = sizes or SIZES
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     if not coalesce:
@@ -33,7 +35,7 @@ def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce,
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     grid = ProcessGrid(dp, pp, rank)
     dp_comm, pp_comm = make_torch_comms(grid)
-    model = MLP(SIZES, grid.stage, pp, GBS).to(f"cuda:{rank}")
+    model = MLP(sizes, grid.stage, pp, GBS).to(f"cuda:{rank}")
     opt = SGD(model.parameters(), LR, arena=model.arena)
     x, y = synthetic_mnist(n=GBS * STEPS)
     ds = Dataset(None, GBS, GBS // dp // N_MU, device=f"cuda:{rank}")
@@ -54,36 +56,37 @@ def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce,
     dist.destroy_process_group()
 
 
-def _cpu_oracle():
+def _cpu_oracle(sizes=None):
+    sizes = sizes or SIZES
     from shallowspeed_b200.dataset import Dataset, synthetic_mnist
     from shallowspeed_b200.layers import MLP
     from shallowspeed_b200.optimizer import SGD
     from shallowspeed_b200.pipe import NaiveParallelSchedule, Worker
 
     x, y = synthetic_mnist(n=GBS * STEPS)
-    model = MLP(SIZES, 0, 1, GBS)
+    model = MLP(sizes, 0, 1, GBS)
     ds = Dataset(None, GBS, GBS // N_MU)
     ds.local_batch_size = GBS
     ds.from_arrays(x, y)
     w = Worker(None, None, model, ds, SGD(model.parameters(), LR, arena=model.arena))
     for b in range(STEPS):
         w.execute(NaiveParallelSchedule(N_MU, 1, 0), b)
-    return [p.data.clone() for p in model.parameters()], MLP(SIZES, 0, 1, GBS)
+    return [p.data.clone() for p in model.parameters()], MLP(sizes, 0, 1, GBS)
 
 
-def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True, two_shot=False):
+def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True, two_shot=False, sizes=None):
     import torch.multiprocessing as mp
 
     world = dp * pp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29800 + (os.getpid() + dp * 7 + pp * 13 + len(sched)) % 150
-    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce, two_shot), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce, two_shot, sizes), nprocs=world, join=True)
     got = [p for s in range(pp) for p in torch.load(tmp_path / f"stage{s}.pt")["params"]]
-    ref, init = _cpu_oracle()
+    ref, init = _cpu_oracle(sizes)
     for p0, a, b in zip(init.parameters(), got, ref):
         upd_err = float(((a - p0.data) - (b - p0.data)).norm() / ((b - p0.data).norm() + 1e-12))
-        assert upd_err < 6e-2, upd_err
+        assert upd_err < 5e-4, upd_err        # default precision fp32 (3xTF32): fp32-level agreement with the CPU oracle
 
 
 @pytest.mark.parametrize("comm_mode", ["fused", "nccl"])
@@ -124,3 +127,13 @@ def test_dp8_fused(tmp_path):
 
 def test_dp2_pp4_gpipe(tmp_path):
     _run(2, 4, "gpipe", "fused", tmp_path)
+
+
+def test_wide_model_dp2_fused(tmp_path):
+    """layers wider than 128: per-layer tcgen05 GEMM kernels (no chain), multi-tile fused wgrad+DP kernels,
+    two-shot single-owner protocol on the 4 MB layers"""
+    _run(2, 1, "naive", "fused", tmp_path, sizes=WIDE)
+
+
+def test_wide_model_dp2_pp2_1f1b(tmp_path):
+    _run(2, 2, "pipedream", "fused", tmp_path, sizes=WIDE)

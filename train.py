@@ -89,8 +89,8 @@ def build_parser():
     p.add_argument("--comm", choices=["fused", "nccl"], default="fused",
                    help="native engine DP path: in-kernel reduction over peer memory, or plain NCCL all-reduce (A/B baseline)")
     p.add_argument("--no-graph", action="store_true", help="native engine: do not capture the step in a CUDA graph")
-    p.add_argument("--precision", choices=["tf32", "fp32"], default="tf32",
-                   help="tensor-core math: single-pass tf32 or 3xTF32 split (fp32-equivalent)")
+    p.add_argument("--precision", choices=["tf32", "fp32"], default="fp32",
+                   help="tensor-core math: fp32 = 3xTF32 split (fp32-equivalent, the reference's contract); tf32 = single pass")
     p.add_argument("--spawn", action="store_true", help="spawn dp*pp local processes instead of relying on torchrun")
     p.add_argument("--log-json", type=str, default=None, help="write JSON-lines metrics here (rank 0)")
     p.add_argument("--save", type=str, default=None, help="directory for per-stage checkpoints at the end of training")
