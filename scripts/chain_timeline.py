@@ -13,7 +13,7 @@ from shallowspeed_b200.parallel.engine import Trainer
 SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
 x, y = synthetic_mnist(n=128 * 4)
 xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
-tr = Trainer(SIZES, use_graph=False)
+tr = Trainer(SIZES, use_graph=False, precision=os.environ.get("PREC", "fp32"))
 for i in range(6):
     tr.step_async(xd[(i % 4) * 128:(i % 4 + 1) * 128], yd[(i % 4) * 128:(i % 4 + 1) * 128])
 tr.synchronize()
