@@ -165,7 +165,7 @@ struct ChainPlan {
     CUtensorMap* maps_dev;
     int grid, smem_bytes;
 };
-bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss);
+bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split = false);
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
                        const float* W_lo = nullptr, const float* x_lo = nullptr);
 void chain_plan_free(ChainPlan* plan);

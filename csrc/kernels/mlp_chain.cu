@@ -55,6 +55,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define DBG(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = gtime(); } while (0)
 
+// SPLIT (3xTF32) is a compile-time switch: the single-pass TF32 instantiation carries none of the lo-twin code
+template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -67,10 +69,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     const int row0 = (p.mu_base + (int)blockIdx.x) * p.mb_rows;                 // first global row of this micro-batch
     const uint32_t b_bytes = (uint32_t)N * 128u;             // one 32-feature panel of an activation tile
     const uint32_t half_stage = (uint32_t)p.kps * (kABytes + b_bytes);    // kps A tiles, then kps X tiles (layer 1)
-    const uint32_t stage_bytes = p.split ? 2u * half_stage : half_stage;  // split: lo twins in the second half
+    const uint32_t stage_bytes = SPLIT ? 2u * half_stage : half_stage;  // split: lo twins in the second half
     const uint32_t stage_b_off = (uint32_t)p.kps * kABytes;
     const uint32_t abuf_bytes = 4u * b_bytes;
-    const uint32_t n_abuf = p.split ? 4u : 2u;                            // hi ping-pong (+ lo ping-pong)
+    const uint32_t n_abuf = SPLIT ? 4u : 2u;                            // hi ping-pong (+ lo ping-pong)
     const uint32_t abuf0 = smem_base + p.stages * stage_bytes;
     const uint32_t lo_off = 2u * abuf_bytes;                              // lo tile of buffer b sits lo_off behind its hi tile
     const uint32_t bar_base = abuf0 + n_abuf * abuf_bytes;
@@ -129,12 +131,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (p.split ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (SPLIT ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
                                 tma_load_2d(a_dst + j * kABytes, p.maps + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                 if (with_x)
                                     tma_load_2d(a_dst + stage_b_off + j * b_bytes, p.maps + 2 * L, full_bar(s), (kb0 + j) * kBlockK, row0);
-                                if (p.split) {
+                                if (SPLIT) {
                                     tma_load_2d(a_dst + half_stage + j * kABytes, p.maps + lo_base + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                     if (with_x)
                                         tma_load_2d(a_dst + half_stage + stage_b_off + j * b_bytes, p.maps + lo_base + 2 * L, full_bar(s),
@@ -155,13 +157,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (p.split ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (SPLIT ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j)
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     tma_load_2d(a_dst + j * kABytes + i * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s), 32 * i,
                                                 (kb0 + j) * kBlockK);
-                                    if (p.split)
+                                    if (SPLIT)
                                         tma_load_2d(a_dst + half_stage + j * kABytes + i * kPanelBytes, p.maps + lo_base + 2 * (l - 1) + 1,
                                                     full_bar(s), 32 * i, (kb0 + j) * kBlockK);
                                 }
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             const uint32_t b_lo = umma_desc_lo(b_j, 16u);
                             const uint32_t a_step = a_mn ? 64u : 2u;
                             const uint32_t ah = a_mn ? mn_hi : k_hi, id = a_mn ? idesc_b : idesc_f;
-                            if (p.split) {                           // lo*hi + hi*lo + hi*hi (raw tiles are the hi parts)
+                            if (SPLIT) {                           // lo*hi + hi*lo + hi*hi (raw tiles are the hi parts)
                                 const uint32_t al_lo = a_lo + (half_stage >> 4);
                                 const uint32_t bl_lo = b_lo + ((b_from_stage ? half_stage : lo_off) >> 4);
 #pragma unroll
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         auto st_tile = [&](uint32_t dst, int n, int feat, float x) {   // operand tile(s) for the next GEMM
             const uint32_t off = (dst - smem_base) + act_smem_off(n, feat, b_bytes);
             *reinterpret_cast<float*>(smem_gen + off) = x;
-            if (p.split) *reinterpret_cast<float*>(smem_gen + off + lo_off) = tf32_lo(x);
+            if (SPLIT) *reinterpret_cast<float*>(smem_gen + off + lo_off) = tf32_lo(x);
         };
         auto publish = [&]() {                               // smem tile complete -> MMA warp may read it
             if (threadIdx.x == 64) DBG(2, 2 * (tmem_waits - 1) + 1);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             if (single) keep[j] = x;
                             else if (m_ok && n < p.mb_rows) {
                                 gout[(int64_t)n * p.act_ld[l] + m] = x;
-                                if (p.split) p.act_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + m] = tf32_lo(x);
+                                if (SPLIT) p.act_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + m] = tf32_lo(x);
                             }
                         }
                     }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         for (int j = 0; j < 16; ++j)
                             if (c_lo + j < p.mb_rows) {
                                 gout[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
-                                if (p.split) p.act_lo[l][(int64_t)(row0 + c_lo + j) * p.act_ld[l] + m] = tf32_lo(keep[j]);
+                                if (SPLIT) p.act_lo[l][(int64_t)(row0 + c_lo + j) * p.act_ld[l] + m] = tf32_lo(keep[j]);
                             }
                     }
                     wbuf ^= 1;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                             gout[(int64_t)n * p.act_ld[l] + k] = zr[k];
                                             p.probs[(int64_t)(row0 + n) * p.ldp + k] = ev[k];
                                             if (p.dz[l] != nullptr) p.dz[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = dzv;
-                                            if (p.split && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
+                                            if (SPLIT && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
                                         }
                                         if (p.do_bwd) st_tile(dst, n, k, dzv);
                                     }
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                         gout[(int64_t)n * p.act_ld[l] + k] = zr[k];
                                         p.probs[(int64_t)(row0 + n) * p.ldp + k] = pr;
                                         if (p.dz[l] != nullptr) p.dz[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = dzv;
-                                        if (p.split && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
+                                        if (SPLIT && p.dz_lo[l] != nullptr) p.dz_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + k] = tf32_lo(dzv);
                                     }
                                     if (p.do_bwd) st_tile(dst, n, k, dzv);
                                 }
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     x = g[(int64_t)n * p.act_ld[L] + m];
                     if (ly.relu && !(y[(int64_t)n * p.act_ld[L] + m] > 0.f)) x = 0.f;
                     g[(int64_t)n * p.act_ld[L] + m] = x;     // the wgrad GEMM reads the masked gradient
-                    if (p.split) p.dz_lo[L][(int64_t)(row0 + n) * p.act_ld[L] + m] = tf32_lo(x);
+                    if (SPLIT) p.dz_lo[L][(int64_t)(row0 + n) * p.act_ld[L] + m] = tf32_lo(x);
                 }
                 st_tile(dst, n, m, x);
             }
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         if (single) keep[j] = x;
                         else if (m_ok && n < p.mb_rows) {
                             gprev[(int64_t)n * p.act_ld[l - 1] + m] = x;
-                            if (p.split) p.dz_lo[l - 1][(int64_t)(row0 + n) * p.act_ld[l - 1] + m] = tf32_lo(x);
+                            if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + n) * p.act_ld[l - 1] + m] = tf32_lo(x);
                         }
                     }
                 }
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     for (int j = 0; j < 16; ++j)
                         if (c_lo + j < p.mb_rows) {
                             gprev[(int64_t)(c_lo + j) * p.act_ld[l - 1] + m] = keep[j];
-                            if (p.split) p.dz_lo[l - 1][(int64_t)(row0 + c_lo + j) * p.act_ld[l - 1] + m] = tf32_lo(keep[j]);
+                            if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + c_lo + j) * p.act_ld[l - 1] + m] = tf32_lo(keep[j]);
                         }
                 }
             }
@@ -503,7 +505,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
 const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int outer, int ld);                 // tc_gemm.cu
 const char* make_tmap_k(CUtensorMap* map, const float* base, int inner, int outer, int ld, int box_outer);   // tc_gemm.cu
 
-bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss) {
+static bool chain_smem_fits(int mb_rows, bool split) {
+    const int n_pad = (mb_rows + 15) / 16 * 16;
+    const int abuf_bytes = 4 * n_pad * 128;
+    const int scratch_bytes = n_pad * kScratchLd * 4 + 256;
+    const int budget = 222 * 1024 - (split ? 4 : 2) * abuf_bytes - scratch_bytes;
+    const int stage_bytes = ((int)kABytes + n_pad * 128) * (split ? 2 : 1);      // kps = 1
+    return budget / stage_bytes >= 2;
+}
+
+bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split) {
+    if (!chain_smem_fits(mb_rows, split)) return false;
     if (n_layers < 1 || n_layers > kChainMaxLayers || mb_rows < 1 || mb_rows > 128) return false;
     for (int l = 0; l < n_layers; ++l) {
         if (layers[l].out > 128) return false;
@@ -567,11 +579,14 @@ void chain_plan_free(ChainPlan* plan) {
 }
 
 cudaError_t chain_configure() {
-    return cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
-    mlp_chain_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+    else mlp_chain_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     return cudaGetLastError();
 }
 

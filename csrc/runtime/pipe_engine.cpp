@@ -277,7 +277,7 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         const int nl = std::min(L_, (int)kChainMaxLayers);
         for (int l = 0; l < nl; ++l) { cl[l].in = cfg_.layers[l].in; cl[l].out = cfg_.layers[l].out; }
         chain_ok_ = L_ >= 1 && L_ <= kChainMaxLayers && !getenv("SSB_NO_CHAIN") &&
-                    chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0);
+                    chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0, cfg_.split != 0);
     }
     instrs_ = instrs;
     mu_of_ = mu_of;
