@@ -196,7 +196,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         dev_step(i)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, period_ms=20) as clk:
         ms_dev = timed(lambda i: dev_step(args.warmup + i), args.steps)
         for i in range(max(3, args.warmup // 4)):
             e2e_step(i)
