@@ -1,0 +1,52 @@
+"""CLI-level smoke tests on the CPU: train.py (sequential and a spawned DP x PP grid through the
+portable VM), checkpoint/resume, and the JSON contract of bench.py's reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, timeout=600):
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    return subprocess.run([sys.executable] + args, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_train_sequential_cpu(tmp_path):
+    log = tmp_path / "m.jsonl"
+    r = _run(["train.py", "--device", "cpu", "--steps", "6", "--no-eval", "--synthetic", "--log-json", str(log),
+              "--save", str(tmp_path / "ck")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    recs = [json.loads(l) for l in open(log)]
+    assert any(rec.get("event") == "epoch" and rec["steps"] == 6 for rec in recs)
+    assert (tmp_path / "ck" / "stage0of1.pt").exists()
+    r2 = _run(["train.py", "--device", "cpu", "--steps", "2", "--no-eval", "--synthetic", "--resume", str(tmp_path / "ck")])
+    assert r2.returncode == 0, r2.stderr[-2000:]
+
+
+def test_train_accepts_reference_flags_and_pipedream():
+    # same three flags as the reference CLI; 'pipedream' (a stub there) works here
+    r = _run(["train.py", "--device", "cpu", "--spawn", "--dp", "2", "--pp", "2", "--schedule", "pipedream", "--steps", "3",
+              "--no-eval", "--synthetic"])
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_train_rejects_bad_grids():
+    r = _run(["train.py", "--device", "cpu", "--dp", "3", "--steps", "1", "--no-eval", "--synthetic"])
+    assert r.returncode != 0            # 128 % 3 != 0 / world size mismatch
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "shallowspeed", "pipe.py")),
+                    reason="reference not installed in baseline/_ref")
+def test_bench_reference_arm_json_contract():
+    r = _run(["bench.py", "--impl", "reference", "--steps", "5", "--warmup", "3"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 5 and d["value"] > 0
+    assert d["config"]["global_batch"] == 128 and d["config"]["n_mubatches"] == 4
