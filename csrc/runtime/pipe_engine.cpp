@@ -1,6 +1,7 @@
 #include "runtime/pipe_engine.h"
 
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -765,7 +766,8 @@ void PipeEngine::finish_build() {
 }
 
 void PipeEngine::exec(const Op& op) {
-    cudaStream_t st = streams_[op.stream];
+    static const bool serialize = getenv("SSB_SERIALIZE") != nullptr;
+    cudaStream_t st = streams_[serialize ? 0 : op.stream];
     switch (op.kind) {
         case OP_WAIT: CUDA_CHECK(cudaStreamWaitEvent(st, events_[op.event], 0)); break;
         case OP_RECORD: CUDA_CHECK(cudaEventRecord(events_[op.event], st)); break;
@@ -809,8 +811,39 @@ void PipeEngine::exec(const Op& op) {
     }
 }
 
+static const char* op_name(int kind) {
+    switch (kind) {
+        case OP_GEMM: return "gemm";
+        case OP_LOSS_HEAD: return "loss_head";
+        case OP_SOFTMAX: return "softmax";
+        case OP_RELU_MASK: return "relu_mask";
+        case OP_SGD: return "sgd";
+        case OP_COMM_GROUP: return "pp_send_recv";
+        case OP_ALLREDUCE: return "dp_allreduce_nccl";
+        case OP_FUSED_DP: return "fused_wgrad_dp";
+        case OP_DP_REDUCE: return "dp_reduce_sgd";
+        case OP_BUMP_EPOCH: return "bump_epoch";
+        case OP_CHAIN: return "mlp_chain";
+        case OP_SPLIT: return "split_lo";
+        case OP_MEMCPY_LOSS: return "loss_d2h";
+        case OP_ARGMAX: return "argmax_correct";
+        case OP_WAIT: return "wait_event";
+        case OP_RECORD: return "record_event";
+    }
+    return "op";
+}
+
+// Eager plan walk.  SSB_NVTX=1 wraps every op in an NVTX range (one range per lowered pipe operation,
+// visible in Nsight Systems); SSB_SERIALIZE=1 is the debugging mode that issues every op on the main
+// stream (no cross-stream concurrency) - the first thing to try when a race is suspected
+// (scripts/sanitize.sh runs compute-sanitizer racecheck / memcheck / synccheck on top of it).
 void PipeEngine::walk(int set) {
-    for (const auto& op : ops_sets_[set]) exec(op);
+    static const bool nvtx = getenv("SSB_NVTX") != nullptr;
+    for (const auto& op : ops_sets_[set]) {
+        if (nvtx) nvtxRangePushA(op_name(op.kind));
+        exec(op);
+        if (nvtx) nvtxRangePop();
+    }
 }
 
 // Inputs of step i go into staging set i % 2 on the COPY stream; the compute graph of that set waits

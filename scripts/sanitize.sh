@@ -1,0 +1,14 @@
+#!/bin/bash
+# Race / memory / sync checking of the native engine under compute-sanitizer (run on a B200, e.g.
+# `gpurun -- bash scripts/sanitize.sh`).  The reference has no sanitizer story at all;
+# here the engine has real concurrency (streams, TMA/async proxy, peer-memory flags), so these are the
+# three standard passes.  Eager mode (--no-graph) so every launch is attributed; tiny step counts because
+# the tools slow kernels down by 10-100x (the device-side spin limit is 4 s).
+set -u
+ARGS="bench.py --steps 2 --warmup 1 --no-graph --pool-batches 4"
+for tool in memcheck racecheck synccheck; do
+    echo "== compute-sanitizer --tool $tool"
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python $ARGS 2>&1 | grep -E "=========|ERROR SUMMARY" | head -40
+done
+echo "== serialized-streams debug mode (SSB_SERIALIZE=1): results must not change"
+SSB_SERIALIZE=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-graph 2>&1 | grep "^{" | cut -c1-160
