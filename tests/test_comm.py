@@ -1,0 +1,51 @@
+"""Process grid + communicator plumbing (CPU)."""
+import threading
+
+import torch
+
+from shallowspeed_b200.parallel.comm import ProcessGrid, SelfComm, ThreadFabric
+
+
+def test_process_grid_matches_reference_rank_mapping():
+    # reference train.py:89-92: dp_comm = Split(color = rank % PP), pp_comm = Split(color = rank // PP)
+    dp, pp = 2, 4
+    for r in range(dp * pp):
+        g = ProcessGrid(dp, pp, r)
+        assert g.stage == r % pp and g.replica == r // pp
+        assert g.dp_group_ranks() == [x for x in range(dp * pp) if x % pp == r % pp]
+        assert g.pp_group_ranks() == [x for x in range(dp * pp) if x // pp == r // pp]
+        assert g.pp_group_ranks() == list(range(g.replica * pp, g.replica * pp + pp))   # adjacent ranks = adjacent GPUs
+
+
+def test_self_comm_is_a_noop_communicator():
+    c = SelfComm()
+    t = torch.ones(4)
+    c.iallreduce(t).wait()
+    assert torch.equal(t, torch.ones(4)) and c.gather("h") == ["h"] and c.Get_size() == 1 and c.Get_rank() == 0
+
+
+def test_thread_fabric_allreduce_is_rank_ordered_and_p2p_works():
+    n = 4
+    fab = ThreadFabric(n)
+    out = {}
+
+    def main(rank):
+        c = fab.comm(rank)
+        t = torch.full((8,), float(rank + 1))
+        c.allreduce(t)
+        out[rank] = t.clone()
+        if rank == 0:
+            c.send(torch.arange(3.0), 1)
+        if rank == 1:
+            buf = torch.empty(3)
+            c.recv(buf, 0)
+            out["recv"] = buf
+        out[("g", rank)] = c.gather(rank * 10)
+
+    th = [threading.Thread(target=main, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join(30) for t in th]
+    for r in range(n):
+        assert torch.equal(out[r], torch.full((8,), 10.0))      # 1+2+3+4, identical bits on every rank
+    assert torch.equal(out["recv"], torch.arange(3.0))
+    assert out[("g", 0)] == [0, 10, 20, 30] and out[("g", 1)] is None
