@@ -70,9 +70,21 @@ def _peer(stage, ins):
 
 @dataclass
 class Trace:
-    """Result of a successful simulation: a global total order of (stage, instr)."""
+    """Result of a successful simulation: one legal total order of (stage, instr) plus the
+    happens-before PARTIAL order every legal execution must respect.
+
+    The partial order is a DAG over items (one item = one compute instruction or one comm group):
+      * program order:   (s, i) -> (s, i+1)
+      * rendezvous:      a group cannot complete before its peer has POSTED the matching operation,
+                         i.e. before the peer finished the item preceding it:
+                         (peer, J-1) -> (s, I)   and   (s, I-1) -> (peer, J)
+      * data:            a receive completes only after the matching send was posted (same edges).
+    ``happens_before(a, b)`` is reachability in that DAG, so it holds in EVERY execution, not just in
+    the simulated linearisation."""
 
     order: list = field(default_factory=list)
+    items: list = field(default_factory=list)          # items[s] = list of _Item
+    edges: dict = field(default_factory=dict)          # (s, i) -> set of (s', i')
 
     def position(self, stage, predicate):
         for i, (s, ins) in enumerate(self.order):
@@ -80,12 +92,43 @@ class Trace:
                 return i
         raise KeyError("instruction not found in trace")
 
+    def _locate(self, stage, predicate):
+        for it in self.items[stage]:
+            for pos, ins in enumerate(it.instrs):
+                if predicate(ins):
+                    return it.index, pos
+        raise KeyError("instruction not found in schedule")
+
+    def _reachable(self, src, dst):
+        if src == dst:
+            return True
+        seen, stack = {src}, [src]
+        while stack:
+            n = stack.pop()
+            for m in self.edges.get(n, ()):
+                if m == dst:
+                    return True
+                if m not in seen:
+                    seen.add(m)
+                    stack.append(m)
+        return False
+
     def happens_before(self, a, b):
-        """a, b = (stage, predicate).  True iff a is ordered before b in EVERY legal
-        execution: checked on the simulated total order plus program order/transitivity
-        through matched messages (the simulation is the least-fixpoint schedule, every
-        real execution is a linear extension of the same partial order)."""
-        return self.position(*a) < self.position(*b)
+        """a, b = (stage, predicate).  True iff a precedes b in every legal execution."""
+        (sa, pa), (sb, pb) = a, b
+        ia, posa = self._locate(sa, pa)
+        ib, posb = self._locate(sb, pb)
+        if sa == sb and ia == ib:
+            return posa < posb
+        if not self.items:
+            return self.position(*a) < self.position(*b)
+        # "a's item completes before b's item completes".  A compute item's only incoming edge is program
+        # order, so for compute b this is the same as "a completes before b starts".
+        return self._reachable((sa, ia), (sb, ib))
+
+    def concurrent(self, a, b):
+        """neither a before b nor b before a: the two may overlap in time."""
+        return not self.happens_before(a, b) and not self.happens_before(b, a)
 
 
 def simulate(schedules: Sequence, check_dataflow: bool = True) -> Trace:
@@ -147,6 +190,22 @@ def simulate(schedules: Sequence, check_dataflow: bool = True) -> Trace:
         return True
 
     trace = Trace()
+    trace.items = items
+    edges = {}
+
+    def add_edge(u, v):
+        if u[1] >= 0:
+            edges.setdefault(u, set()).add(v)
+
+    for st in range(S):
+        for it in items[st]:
+            if it.index + 1 < len(items[st]):
+                add_edge((st, it.index), (st, it.index + 1))
+    for (src, dst, nmsg), i_send in send_at.items():
+        j_recv = recv_at[(src, dst, nmsg)]
+        add_edge((dst, j_recv - 1), (src, i_send))      # the send completes only once the receive is posted
+        add_edge((src, i_send - 1), (dst, j_recv))      # the receive completes only once the send is posted
+    trace.edges = edges
     total = sum(len(x) for x in items)
     done = 0
     while done < total:

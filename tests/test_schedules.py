@@ -154,3 +154,16 @@ def test_instruction_encoding_roundtrip():
         op, b, mu = encode(ins)
         assert OPCODE_TO_CLS[op] is type(ins)
         assert b == getattr(ins, "buffer_id", -1) and mu == getattr(ins, "mubatch_id", -1)
+
+
+def test_happens_before_is_a_partial_order_not_a_linearisation():
+    # GPipe, 3 stages: forward of mubatch 1 on stage 0 and forward of mubatch 0 on stage 2 are unordered
+    # (they overlap in the pipeline) - a single simulated total order would wrongly order them.
+    tr = validate(GPipeSchedule, 4, 3)
+    assert tr.concurrent((0, _F(2)), (2, _F(0)))
+    assert tr.happens_before((0, _F(0)), (2, _F(0)))          # data dependence through two sends
+    assert not tr.happens_before((2, _F(0)), (0, _F(0)))
+    # 1F1B steady state: stage 0's forward of mubatch 3 may overlap stage 1's backward of mubatch 0 ...
+    tr = validate(PipeDreamSchedule, 8, 2)
+    assert tr.happens_before((1, _B(0)), (0, _B(0)))          # ... but gradients still flow last -> first
+    assert tr.happens_before((0, _F(1)), (1, _F(1)))
