@@ -126,6 +126,62 @@ class Trace:
         # order, so for compute b this is the same as "a completes before b starts".
         return self._reachable((sa, ia), (sb, ib))
 
+    def timeline(self, cost=None):
+        """Earliest-finish (critical path) times of every item under a cost model.
+
+        ``cost(stage, instr) -> float`` gives the duration of a compute instruction (default: Forward 1,
+        Backward 2, everything else 0); comm groups take no time of their own but inherit the rendezvous
+        dependencies.  Returns ``{(stage, item_index): (start, finish)}`` - the schedule an ideal executor with
+        infinitely fast links would achieve, which is what the bubble fractions quoted for GPipe / 1F1B
+        assume."""
+        if cost is None:
+            def cost(_s, ins):
+                if isinstance(ins, Forward):
+                    return 1.0
+                if isinstance(ins, (BackwardGradAcc, BackwardGradAllReduce)):
+                    return 2.0
+                return 0.0
+        preds = {}
+        for u, vs in self.edges.items():
+            for v in vs:
+                preds.setdefault(v, []).append(u)
+        finish, out = {}, {}
+        # the simulated total order is a topological order of the item DAG
+        seen = []
+        for s, ins in self.order:
+            for it in self.items[s]:
+                if it.instrs[0] is ins:
+                    seen.append((s, it.index))
+        pending = list(seen)
+        guard = 0
+        while pending:
+            guard += 1
+            if guard > 4 * len(seen) * len(seen) + 16:
+                raise ScheduleError("timeline: dependency cycle")
+            node = pending.pop(0)
+            ps = preds.get(node, [])
+            if any(p not in finish for p in ps):
+                pending.append(node)
+                continue
+            start = max([finish[p] for p in ps], default=0.0)
+            it = self.items[node[0]][node[1]]
+            dur = sum(cost(node[0], i) for i in it.instrs) if it.kind == "compute" else 0.0
+            finish[node] = start + dur
+            out[node] = (start, start + dur)
+        return out
+
+    def makespan(self, cost=None):
+        return max(f for _, f in self.timeline(cost).values())
+
+    def bubble_fraction(self, cost=None):
+        """1 - (busy time of the busiest stage) / makespan under the cost model."""
+        tl = self.timeline(cost)
+        span = max(f for _, f in tl.values())
+        busy = {}
+        for (s, _i), (a, b) in tl.items():
+            busy[s] = busy.get(s, 0.0) + (b - a)
+        return 1.0 - max(busy.values()) / span if span > 0 else 0.0
+
     def concurrent(self, a, b):
         """neither a before b nor b before a: the two may overlap in time."""
         return not self.happens_before(a, b) and not self.happens_before(b, a)

@@ -167,3 +167,35 @@ def test_happens_before_is_a_partial_order_not_a_linearisation():
     tr = validate(PipeDreamSchedule, 8, 2)
     assert tr.happens_before((1, _B(0)), (0, _B(0)))          # ... but gradients still flow last -> first
     assert tr.happens_before((0, _F(1)), (1, _F(1)))
+
+
+@pytest.mark.parametrize("M,S", [(4, 2), (8, 4), (16, 4), (5, 3)])
+def test_bubble_fraction_matches_the_textbook_formula(M, S):
+    # with F=1, B=2 and free links GPipe and 1F1B both have bubble (S-1)/(M+S-1); naive runs one stage at a time
+    for cls in (GPipeSchedule, PipeDreamSchedule):
+        tr = validate(cls, M, S)
+        assert tr.makespan() == pytest.approx(3.0 * (M + S - 1))
+        assert tr.bubble_fraction() == pytest.approx((S - 1) / (M + S - 1))
+    from shallowspeed_b200.parallel.schedules import NaiveParallelSchedule
+    tr = validate(NaiveParallelSchedule, M, S)
+    assert tr.makespan() == pytest.approx(3.0 * M * S)
+    assert tr.bubble_fraction() == pytest.approx(1 - 1 / S)
+
+
+def test_1f1b_same_makespan_less_activation_memory():
+    from shallowspeed_b200.parallel.validate import max_in_flight
+    M, S = 16, 4
+    assert validate(PipeDreamSchedule, M, S).makespan() == validate(GPipeSchedule, M, S).makespan()
+    assert max_in_flight(PipeDreamSchedule(M, S, 0)) == S
+    assert max_in_flight(GPipeSchedule(M, S, 0)) == M
+
+
+def test_render_schedule_svg(tmp_path):
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "s.svg"
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "render_schedule.py"), "--schedule", "1f1b", "--pp", "2",
+                    "--n-mubatches", "4", "-o", str(out)], check=True, timeout=300)
+    txt = out.read_text()
+    assert txt.startswith("<svg") and "B3*<" in txt  # 1F1B finishes on the last micro-batch
+    assert txt.count(">F") == 9  # 8 forward boxes + the legend
