@@ -50,6 +50,16 @@ public:
         cudaStreamSynchronize(nullptr);
         cudaFree(buf);
     }
+    // failure handling: async error state, and a non-blocking teardown that also unblocks the peers
+    std::string async_error() {
+        ncclResult_t r = ncclSuccess;
+        NCCL_OK(ncclCommGetAsyncError(comm_, &r));
+        return r == ncclSuccess ? std::string() : std::string(ncclGetErrorString(r));
+    }
+    void abort() {
+        if (comm_) ncclCommAbort(comm_);
+        comm_ = nullptr;
+    }
     ncclComm_t get() const { return comm_; }
     int nranks() const { return nranks_; }
     int rank() const { return rank_; }
@@ -130,6 +140,11 @@ public:
     }
     void run() { engine_->run(); }
     void synchronize() { engine_->synchronize(); }
+    bool wait(double timeout_s) {
+        py::gil_scoped_release nogil;
+        return engine_->wait(timeout_s);
+    }
+    std::string comm_status() { return engine_->comm_status(); }
     float last_loss() { return engine_->last_loss(); }
     float prev_loss() { return engine_->prev_loss(); }
     int count_correct() { return engine_->count_correct(); }
@@ -168,6 +183,8 @@ void bind_runtime(py::module_& m) {
         .def_static("unique_id", &NcclComm::unique_id)
         .def(py::init<const std::string&, int, int>())
         .def("warmup", &NcclComm::warmup)
+        .def("async_error", &NcclComm::async_error)
+        .def("abort", &NcclComm::abort)
         .def("nranks", &NcclComm::nranks)
         .def("rank", &NcclComm::rank);
     py::class_<PyDpContext, std::shared_ptr<PyDpContext>>(m, "DpContext")
@@ -185,6 +202,8 @@ void bind_runtime(py::module_& m) {
         .def("stage_inputs", &PyEngine::stage_inputs)
         .def("run", &PyEngine::run)
         .def("synchronize", &PyEngine::synchronize)
+        .def("wait", &PyEngine::wait)
+        .def("comm_status", &PyEngine::comm_status)
         .def("last_loss", &PyEngine::last_loss)
         .def("prev_loss", &PyEngine::prev_loss)
         .def("count_correct", &PyEngine::count_correct)

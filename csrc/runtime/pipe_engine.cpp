@@ -4,6 +4,8 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <sstream>
 #include <stdexcept>
@@ -879,6 +881,34 @@ void PipeEngine::run() {
 }
 
 void PipeEngine::synchronize() { CUDA_CHECK(cudaStreamSynchronize(streams_[0])); }
+
+// Failure detection: bounded wait for the step in flight.  Returns true when the main stream drained,
+// false when `timeout_s` elapsed first (a peer died, a schedule bug, a lost NCCL message ...).  A sticky
+// CUDA error (e.g. the __trap() of a device-flag spin that hit its own bound) surfaces as an exception.
+bool PipeEngine::wait(double timeout_s) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(streams_[0]);
+        if (e == cudaSuccess) return true;
+        if (e != cudaErrorNotReady) CUDA_CHECK(e);
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return false;
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+}
+
+// What the communicators know about a stalled step (ncclCommGetAsyncError), for the watchdog's report.
+std::string PipeEngine::comm_status() const {
+    std::ostringstream os;
+    auto one = [&](const char* name, ncclComm_t c) {
+        if (!c) return;
+        ncclResult_t r = ncclSuccess;
+        const ncclResult_t q = ncclCommGetAsyncError(c, &r);
+        os << name << "=" << (q == ncclSuccess ? ncclGetErrorString(r) : ncclGetErrorString(q)) << " ";
+    };
+    one("pp_comm", pp_comm_);
+    one("dp_comm", dp_comm_);
+    return os.str();
+}
 
 float PipeEngine::last_loss() {
     synchronize();

@@ -98,6 +98,8 @@ public:
     void stage_inputs(const float* x, const float* y, bool from_host);
     void run();                       // one step (graph launch or eager plan walk) on the main stream
     void synchronize();
+    bool wait(double timeout_s);      // watchdog: false if the step in flight did not finish in time
+    std::string comm_status() const;  // NCCL async error state of the attached communicators
     float last_loss();                // sum of the micro-batch losses of the most recent step (synchronizes)
     float prev_loss();                // loss of the step before the most recently launched one (pipelined readback)
     int count_correct();              // inference: # argmax matches accumulated since reset

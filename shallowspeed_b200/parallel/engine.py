@@ -21,6 +21,20 @@ from .validate import simulate
 DP_MODE = {"none": 0, "nccl": 1, "fused": 2}
 
 
+class StepTimeout(RuntimeError):
+    """A training step did not finish within the watchdog's bound (dead peer, lost message, schedule bug)."""
+
+
+def watchdog_seconds(explicit=None):
+    """Watchdog bound in seconds: the explicit argument, else ``SSB_WATCHDOG_S``, else None (disabled)."""
+    import os
+
+    if explicit is not None:
+        return float(explicit) if explicit > 0 else None
+    env = os.environ.get("SSB_WATCHDOG_S", "")
+    return float(env) if env and float(env) > 0 else None
+
+
 def _C():
     from .. import _C as mod
 
@@ -166,6 +180,23 @@ class NativeWorker:
         for e in self._engines.values():
             e.synchronize()
 
+    # ------------------------------------------------------------------ failure detection
+    def guard(self, eng, timeout_s, what="step"):
+        """Bounded wait for the work in flight on ``eng``.  On timeout: report what the communicators know,
+        abort them (so the peers blocked in the matching operations fail instead of hanging with us) and raise
+        ``StepTimeout``.  Device-side spins (fused DP flags) carry their own bound and surface as CUDA errors."""
+        if timeout_s is None or eng.wait(float(timeout_s)):
+            return
+        status = eng.comm_status()
+        self.abort_comms()
+        raise StepTimeout(f"{what} did not finish within {timeout_s:g} s on stage {self.stage_id} "
+                          f"(dp rank {self.dp_comm.Get_rank()}); communicators: {status or 'none'}; plan: {eng.describe()[:200]}")
+
+    def abort_comms(self):
+        for nc in (self._pp_nccl, self._dp_nccl):
+            if nc is not None:
+                nc.abort()
+
     def sync_to_model(self):
         """Weights live in the model's arena already; just drain the streams."""
         self.synchronize()
@@ -189,7 +220,7 @@ class Trainer:
 
     def __init__(self, layer_sizes, global_batch_size=128, n_mubatches=4, lr=0.006, schedule="naive",
                  dp_comm=None, pp_comm=None, grid: Optional[ProcessGrid] = None, comm_mode="fused",
-                 use_graph=True, device=None, seed_mode="shape", precision="fp32"):
+                 use_graph=True, device=None, seed_mode="shape", precision="fp32", watchdog_s=None):
         from ..models.mlp import MLP
         from ..optimizer import SGD
         from .schedules import SCHEDULE_NAME_TO_CLS
@@ -213,6 +244,7 @@ class Trainer:
         self.engine = self.worker.engine_for(self.schedule)
         self.is_first, self.is_last = self.schedule.is_first_stage, self.schedule.is_last_stage
         self._steps = 0
+        self.watchdog_s = watchdog_seconds(watchdog_s)   # None = plain stream synchronisation (default)
 
     def step_async(self, x_host, y_host):
         self.engine.stage_inputs(x_host if self.is_first else None, y_host if self.is_last else None)
@@ -222,6 +254,8 @@ class Trainer:
     def step(self, x_host, y_host):
         """Run one step and return its loss (synchronises with the device)."""
         self.step_async(x_host, y_host)
+        if self.watchdog_s is not None:
+            self.worker.guard(self.engine, self.watchdog_s, what=f"step {self._steps}")
         return self.engine.last_loss() if self.is_last else None
 
     def step_pipelined(self, x_host, y_host):
@@ -241,4 +275,6 @@ class Trainer:
         return self.engine.last_loss() if self.is_last else None
 
     def synchronize(self):
+        if self.watchdog_s is not None:
+            self.worker.guard(self.engine, self.watchdog_s, what="synchronize")
         self.engine.synchronize()

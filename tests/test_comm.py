@@ -1,6 +1,8 @@
 """Process grid + communicator plumbing (CPU)."""
 import threading
 
+import pytest
+
 import torch
 
 from shallowspeed_b200.parallel.comm import ProcessGrid, SelfComm, ThreadFabric
@@ -49,3 +51,44 @@ def test_thread_fabric_allreduce_is_rank_ordered_and_p2p_works():
         assert torch.equal(out[r], torch.full((8,), 10.0))      # 1+2+3+4, identical bits on every rank
     assert torch.equal(out["recv"], torch.arange(3.0))
     assert out[("g", 0)] == [0, 10, 20, 30] and out[("g", 1)] is None
+
+
+def test_watchdog_reports_and_aborts_on_timeout(monkeypatch):
+    """Failure detection (host side): a step that never finishes raises StepTimeout, names the rank and
+    aborts the native communicators so peers do not hang with it."""
+    from shallowspeed_b200.parallel import engine as E
+
+    monkeypatch.delenv("SSB_WATCHDOG_S", raising=False)
+    assert E.watchdog_seconds() is None and E.watchdog_seconds(0) is None and E.watchdog_seconds(2) == 2.0
+    monkeypatch.setenv("SSB_WATCHDOG_S", "7.5")
+    assert E.watchdog_seconds() == 7.5 and E.watchdog_seconds(1) == 1.0
+
+    class FakeEngine:
+        def __init__(self, done):
+            self.done, self.waited = done, None
+
+        def wait(self, t):
+            self.waited = t
+            return self.done
+
+        def comm_status(self):
+            return "pp_comm=unhandled cuda error "
+
+        def describe(self):
+            return "plan"
+
+    class FakeNccl:
+        aborted = False
+
+        def abort(self):
+            self.aborted = True
+
+    w = E.NativeWorker.__new__(E.NativeWorker)
+    w.stage_id, w.dp_comm, w._pp_nccl, w._dp_nccl = 1, SelfComm(), FakeNccl(), None
+    ok = FakeEngine(True)
+    w.guard(ok, 3.0)
+    assert ok.waited == 3.0 and not w._pp_nccl.aborted
+    w.guard(FakeEngine(False), None)            # disabled watchdog never waits
+    with pytest.raises(E.StepTimeout, match="stage 1.*unhandled cuda error"):
+        w.guard(FakeEngine(False), 0.01, what="step 12")
+    assert w._pp_nccl.aborted

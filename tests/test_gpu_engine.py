@@ -169,3 +169,17 @@ def test_trainer_end_to_end_from_pinned_host():
             losses.append(tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]))
     assert all(l == l for l in losses)
     assert losses[-1] < 0.85 * losses[0]
+
+
+def test_trainer_watchdog_passes_through_when_healthy():
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=256)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    plain, guarded = Trainer(SIZES, lr=0.1), Trainer(SIZES, lr=0.1, watchdog_s=60.0)
+    for i in range(2):
+        a = plain.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128])
+        b = guarded.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128])
+        assert a == b
+    assert guarded.engine.wait(1.0) and guarded.engine.comm_status() == ""

@@ -91,6 +91,9 @@ def build_parser():
     p.add_argument("--no-graph", action="store_true", help="native engine: do not capture the step in a CUDA graph")
     p.add_argument("--precision", choices=["tf32", "fp32"], default="fp32",
                    help="tensor-core math: fp32 = 3xTF32 split (fp32-equivalent, the reference's contract); tf32 = single pass")
+    p.add_argument("--watchdog-s", type=float, default=None,
+                   help="native engine: abort (and tear the NCCL communicators down) if an epoch's work is still in "
+                        "flight after this many seconds; default: SSB_WATCHDOG_S or disabled")
     p.add_argument("--spawn", action="store_true", help="spawn dp*pp local processes instead of relying on torchrun")
     p.add_argument("--log-json", type=str, default=None, help="write JSON-lines metrics here (rank 0)")
     p.add_argument("--save", type=str, default=None, help="directory for per-stage checkpoints at the end of training")
@@ -204,6 +207,10 @@ def main(args):
         for batch_id in range(steps_this_epoch):
             worker.execute(schedule, batch_id)
             step += 1
+        if engine == "native":
+            from shallowspeed_b200.parallel.engine import watchdog_seconds
+
+            worker.guard(worker._last_engine, watchdog_seconds(args.watchdog_s), what=f"epoch {epoch}")
         if device_type == "cuda":
             torch.cuda.synchronize()
         dt = time.time() - t_epoch
