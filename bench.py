@@ -204,6 +204,13 @@ def run_ours(args):
         losses.append(trainer.flush())
     ms_dev, ms_e2e = max_over_ranks(ms_dev, dev), max_over_ranks(ms_e2e, dev)
     clocks = clk.summary()
+    comm = None
+    if eng.comm_timing_enabled():   # SSB_COMM_TIMING=1: eager walk with timing events around comm ops and comm waits
+        barrier()
+        dev_step(0)
+        exposed_ms, busy_ms = eng.comm_timing()
+        comm = {"exposed_ms_per_step": max_over_ranks(exposed_ms, dev), "busy_ms_per_step": max_over_ranks(busy_ms, dev),
+                "note": "eager (no CUDA graph) diagnostic run; throughput numbers of this run are not bench values"}
 
     if dp > 1:   # replicas must still be bit-identical after the run
         from shallowspeed_b200.utils import assert_sync, get_model_hash
@@ -225,11 +232,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": kps * args.steps,
             "clocks": clocks,
+            **({"comm": comm} if comm is not None else {}),
             "config": {"model": "MLP " + "-".join(str(v) for v in (sizes if len(sizes) <= 9 else sizes[:2] + ["..."] + sizes[-2:])),
                        "global_batch": gbs, "per_replica_batch": local_bs,
                        "n_mubatches": args.n_mubatches, "seq_len": None,
                        "parallelism": f"dp{dp}" + (f"xpp{args.pp}" if args.pp > 1 else ""), "schedule": args.schedule,
-                       "dp_comm": args.comm if dp > 1 else "none", "cuda_graph": not args.no_graph,
+                       "dp_comm": args.comm if dp > 1 else "none", "cuda_graph": (not args.no_graph) and comm is None,
                        "kernels_per_step": kps, "graph_nodes": int(eng.graph_nodes()),
                        "l2": f"inputs cycle through a pool of {pool} distinct batches ({pool * h2d / 1e6:.0f} MB > 126 MB L2); "
                              "the 0.7 MB of weights are legitimately L2-resident across steps",

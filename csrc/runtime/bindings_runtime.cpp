@@ -145,6 +145,8 @@ public:
         return engine_->wait(timeout_s);
     }
     std::string comm_status() { return engine_->comm_status(); }
+    std::pair<double, double> comm_timing() { return engine_->comm_timing(); }
+    bool comm_timing_enabled() { return engine_->comm_timing_enabled(); }
     float last_loss() { return engine_->last_loss(); }
     float prev_loss() { return engine_->prev_loss(); }
     int count_correct() { return engine_->count_correct(); }
@@ -204,6 +206,8 @@ void bind_runtime(py::module_& m) {
         .def("synchronize", &PyEngine::synchronize)
         .def("wait", &PyEngine::wait)
         .def("comm_status", &PyEngine::comm_status)
+        .def("comm_timing", &PyEngine::comm_timing)
+        .def("comm_timing_enabled", &PyEngine::comm_timing_enabled)
         .def("last_loss", &PyEngine::last_loss)
         .def("prev_loss", &PyEngine::prev_loss)
         .def("count_correct", &PyEngine::count_correct)

@@ -64,6 +64,7 @@ PipeEngine::~PipeEngine() {
     }
     cudaStreamDestroy(copy_stream_);
     for (auto e : events_) cudaEventDestroy(e);
+    for (auto e : timing_events_) cudaEventDestroy(e);
     for (auto s : streams_) cudaStreamDestroy(s);
     for (auto& cp : chain_plans_) chain_plan_free(&cp);
     for (auto p : owned_) cudaFree(p);
@@ -242,8 +243,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
 
 void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
     if (built_) throw std::runtime_error("PipeEngine::build called twice");
-    const int M = cfg_.n_mu, mb = cfg_.mb_rows, n = (int)instrs.size();
-    const bool first = cfg_.is_first, last = cfg_.is_last;
+    const int M = cfg_.n_mu, n = (int)instrs.size();
 
     // ---- resolve which micro-batch every comm instruction carries
     std::vector<int> mu_of(n, -1);
@@ -754,7 +754,8 @@ void PipeEngine::finish_build() {
     }
     if (!chain_plans_.empty()) CUDA_CHECK(chain_configure());
     if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
-    if (cfg_.use_graph) {
+    comm_timing_ = getenv("SSB_COMM_TIMING") != nullptr;   // needs timing events between ops: eager plan walk
+    if (cfg_.use_graph && !comm_timing_) {
         for (int set = 0; set < 2; ++set) {
             CUDA_CHECK(cudaStreamBeginCapture(streams_[0], cudaStreamCaptureModeThreadLocal));
             walk(set);
@@ -767,9 +768,13 @@ void PipeEngine::finish_build() {
     }
 }
 
-void PipeEngine::exec(const Op& op) {
+cudaStream_t PipeEngine::stream_of(const Op& op) const {
     static const bool serialize = getenv("SSB_SERIALIZE") != nullptr;
-    cudaStream_t st = streams_[serialize ? 0 : op.stream];
+    return streams_[serialize ? 0 : op.stream];
+}
+
+void PipeEngine::exec(const Op& op) {
+    cudaStream_t st = stream_of(op);
     switch (op.kind) {
         case OP_WAIT: CUDA_CHECK(cudaStreamWaitEvent(st, events_[op.event], 0)); break;
         case OP_RECORD: CUDA_CHECK(cudaEventRecord(events_[op.event], st)); break;
@@ -839,13 +844,64 @@ static const char* op_name(int kind) {
 // visible in Nsight Systems); SSB_SERIALIZE=1 is the debugging mode that issues every op on the main
 // stream (no cross-stream concurrency) - the first thing to try when a race is suspected
 // (scripts/sanitize.sh runs compute-sanitizer racecheck / memcheck / synccheck on top of it).
+//
+// SSB_COMM_TIMING=1 (eager only) brackets with timing events (a) every communication op on its own
+// stream  -> "busy" time of the links, and (b) every wait of a COMPUTE stream on an event recorded by a
+// communication stream -> the time compute actually stalled on communication ("exposed").
 void PipeEngine::walk(int set) {
     static const bool nvtx = getenv("SSB_NVTX") != nullptr;
+    const bool timing = comm_timing_;
+    std::vector<int> recorded_on;
+    size_t next_ev = 0;
+    auto tev = [&]() {
+        if (next_ev == timing_events_.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            timing_events_.push_back(e);
+        }
+        return timing_events_[next_ev++];
+    };
+    if (timing) {
+        recorded_on.assign(events_.size(), -1);
+        exposed_pairs_.clear();
+        busy_pairs_.clear();
+    }
+    auto is_comm_stream = [&](int s) { return s == s_comm_ || s == s_dp_; };
     for (const auto& op : ops_sets_[set]) {
         if (nvtx) nvtxRangePushA(op_name(op.kind));
+        bool bracket = false, busy = false;
+        if (timing) {
+            if (op.kind == OP_RECORD) recorded_on[op.event] = op.stream;
+            const bool comm_op = op.kind == OP_COMM_GROUP || op.kind == OP_ALLREDUCE || op.kind == OP_DP_REDUCE ||
+                                 op.kind == OP_FUSED_DP;
+            busy = comm_op;
+            bracket = comm_op || (op.kind == OP_WAIT && !is_comm_stream(op.stream) && recorded_on[op.event] >= 0 &&
+                                  is_comm_stream(recorded_on[op.event]));
+        }
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (bracket) {
+            a = tev();
+            CUDA_CHECK(cudaEventRecord(a, stream_of(op)));
+        }
         exec(op);
+        if (bracket) {
+            b = tev();
+            CUDA_CHECK(cudaEventRecord(b, stream_of(op)));
+            (busy ? busy_pairs_ : exposed_pairs_).push_back({a, b});
+        }
         if (nvtx) nvtxRangePop();
     }
+}
+
+// (exposed_ms, busy_ms) of the most recent step walked with SSB_COMM_TIMING=1; synchronizes.
+std::pair<double, double> PipeEngine::comm_timing() {
+    synchronize();
+    CUDA_CHECK(cudaDeviceSynchronize());
+    double exposed = 0.0, busy = 0.0;
+    float ms = 0.f;
+    for (auto& pr : exposed_pairs_) { CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second)); exposed += ms; }
+    for (auto& pr : busy_pairs_) { CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second)); busy += ms; }
+    return {exposed, busy};
 }
 
 // Inputs of step i go into staging set i % 2 on the COPY stream; the compute graph of that set waits

@@ -21,6 +21,7 @@
 #include <functional>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "kernels/kernels.h"
@@ -100,6 +101,9 @@ public:
     void synchronize();
     bool wait(double timeout_s);      // watchdog: false if the step in flight did not finish in time
     std::string comm_status() const;  // NCCL async error state of the attached communicators
+    // SSB_COMM_TIMING=1: (ms the compute streams stalled on communication, ms the comm ops were busy) of the last step
+    std::pair<double, double> comm_timing();
+    bool comm_timing_enabled() const { return comm_timing_; }
     float last_loss();                // sum of the micro-batch losses of the most recent step (synchronizes)
     float prev_loss();                // loss of the step before the most recently launched one (pipelined readback)
     int count_correct();              // inference: # argmax matches accumulated since reset
@@ -133,6 +137,7 @@ private:
     int emit_record(int stream);
     void walk(int set);
     void exec(const Op& op);
+    cudaStream_t stream_of(const Op& op) const;
 
     EngineConfig cfg_;
     float *W_, *G_;
@@ -158,6 +163,9 @@ private:
 
     std::vector<cudaStream_t> streams_;
     std::vector<cudaEvent_t> events_;
+    std::vector<cudaEvent_t> timing_events_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exposed_pairs_, busy_pairs_;
+    bool comm_timing_ = false;
     std::vector<GemmPlan> gemms_;
     std::vector<FusedDpPlan> dp_plans_;
     std::vector<ChainPlan> chain_plans_;
