@@ -170,30 +170,3 @@ def test_trainer_end_to_end_from_pinned_host():
     assert all(l == l for l in losses)
     assert losses[-1] < 0.85 * losses[0]
 
-
-def test_trainer_watchdog_passes_through_when_healthy():
-    from shallowspeed_b200.dataset import synthetic_mnist
-    from shallowspeed_b200.parallel.engine import Trainer
-
-    x, y = synthetic_mnist(n=256)
-    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    plain, guarded = Trainer(SIZES, lr=0.1), Trainer(SIZES, lr=0.1, watchdog_s=60.0)
-    for i in range(2):
-        a = plain.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128])
-        b = guarded.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128])
-        assert a == b
-    assert guarded.engine.wait(1.0) and guarded.engine.comm_status() == ""
-
-
-def test_comm_timing_mode_is_eager_and_reports_zero_without_communication(monkeypatch):
-    from shallowspeed_b200.dataset import synthetic_mnist
-    from shallowspeed_b200.parallel.engine import Trainer
-
-    x, y = synthetic_mnist(n=128)
-    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    ref = Trainer(SIZES, lr=0.1).step(xh, yh)
-    monkeypatch.setenv("SSB_COMM_TIMING", "1")
-    tr = Trainer(SIZES, lr=0.1)
-    assert tr.engine.comm_timing_enabled() and int(tr.engine.graph_nodes()) == 0
-    assert tr.step(xh, yh) == ref
-    assert tr.engine.comm_timing() == (0.0, 0.0)
