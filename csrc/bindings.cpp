@@ -45,9 +45,28 @@ static void split_lo(const Tensor& x, Tensor& lo) {
     cuda_ok(ssb::launch_split_lo(x.data_ptr<float>(), lo.data_ptr<float>(), n, cur_stream()), "split_lo");
 }
 
+// k_splits: 0 / 1 = plain kernel, -1 = let the planner decide, k >= 2 = force k (must not leave a split empty).
+// The workspace and the tile counters are torch tensors owned by the caller's scope (stream-ordered reuse).
+static void enable_splitk(ssb::GemmPlan& plan, int64_t k_splits, const Tensor& like, Tensor& ws, Tensor& counters) {
+    if (k_splits == 0 || k_splits == 1) return;
+    int splits = (int)k_splits;
+    if (k_splits < 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        splits = ssb::gemm_splitk_choice(plan, sms);
+        if (splits < 2) return;
+    }
+    ws = torch::empty({(int64_t)ssb::gemm_splitk_workspace_floats(plan, splits)}, like.options());
+    counters = torch::zeros({(int64_t)plan.grid.x * plan.grid.y}, like.options().dtype(torch::kInt32));
+    const char* err = ssb::gemm_plan_enable_splitk(&plan, splits, ws.data_ptr<float>(),
+                                                   reinterpret_cast<unsigned int*>(counters.data_ptr<int32_t>()));
+    TORCH_CHECK(err == nullptr, "split-K: ", err ? err : "");
+}
+
 static void linear_fwd(const Tensor& x, const Tensor& W, const c10::optional<Tensor>& bias, int64_t bias_stride,
                        bool relu, Tensor& y, const c10::optional<Tensor>& W_lo, const c10::optional<Tensor>& x_lo,
-                       const c10::optional<Tensor>& y_lo) {
+                       const c10::optional<Tensor>& y_lo, int64_t k_splits) {
     check_mat(x, "x"); check_mat(W, "W"); check_mat(y, "y");
     const int rows = x.size(0), in = x.size(1), out = W.size(0);
     TORCH_CHECK(W.size(1) == in && y.size(0) == rows && y.size(1) == out, "linear_fwd: shape mismatch");
@@ -58,12 +77,15 @@ static void linear_fwd(const Tensor& x, const Tensor& W, const c10::optional<Ten
                                          bias.has_value() ? bias->data_ptr<float>() : nullptr, (int)bias_stride, relu,
                                          make_lo(W_lo, x_lo, y_lo));
     TORCH_CHECK(err == nullptr, "linear_fwd: ", err ? err : "");
+    Tensor ws, counters;
+    enable_splitk(plan, k_splits, x, ws, counters);
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_fwd launch");
 }
 
 // dx[rows, in] = (dz @ W) * (mask > 0)
 static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<Tensor>& mask, Tensor& dx,
-                         const c10::optional<Tensor>& W_lo, const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& dx_lo) {
+                         const c10::optional<Tensor>& W_lo, const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& dx_lo,
+                         int64_t k_splits) {
     check_mat(dz, "dz"); check_mat(W, "W"); check_mat(dx, "dx");
     const int rows = dz.size(0), out = dz.size(1), in = W.size(1);
     TORCH_CHECK(W.size(0) == out && dx.size(0) == rows && dx.size(1) == in, "linear_dgrad: shape mismatch");
@@ -75,6 +97,8 @@ static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<
                                            mask.has_value() ? mask->data_ptr<float>() : nullptr,
                                            mask.has_value() ? ld_of(*mask) : 0, make_lo(W_lo, dz_lo, dx_lo));
     TORCH_CHECK(err == nullptr, "linear_dgrad: ", err ? err : "");
+    Tensor ws, counters;
+    enable_splitk(plan, k_splits, dz, ws, counters);
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_dgrad launch");
 }
 
@@ -148,8 +172,11 @@ static void argmax_correct(const Tensor& pred, const Tensor& target, Tensor& cor
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "shallowspeed_b200 native module: sm_100a kernels + C++ pipeline runtime";
     m.def("split_lo", &split_lo);
-    m.def("linear_fwd", &linear_fwd);
-    m.def("linear_dgrad", &linear_dgrad);
+    m.def("linear_fwd", &linear_fwd, py::arg("x"), py::arg("W"), py::arg("bias"), py::arg("bias_stride"), py::arg("relu"),
+          py::arg("y"), py::arg("W_lo") = py::none(), py::arg("x_lo") = py::none(), py::arg("y_lo") = py::none(),
+          py::arg("k_splits") = 0);
+    m.def("linear_dgrad", &linear_dgrad, py::arg("dz"), py::arg("W"), py::arg("mask"), py::arg("dx"),
+          py::arg("W_lo") = py::none(), py::arg("dz_lo") = py::none(), py::arg("dx_lo") = py::none(), py::arg("k_splits") = 0);
     m.def("linear_wgrad", &linear_wgrad);
     m.def("loss_head", &loss_head);
     m.def("softmax_grad", &softmax_grad);

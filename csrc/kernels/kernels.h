@@ -46,6 +46,11 @@ struct GemmParams {
     // also emit the lo twin of their output so the next GEMM can consume it
     int split;
     float* out_lo;
+    // split-K (FWD / DGRAD, see gemm_plan_enable_splitk): blockIdx.z owns a k-range, partial tiles go through
+    // `partial` [tile][split][block_n][128], the last arriver at tile_counter[tile] reduces + runs the epilogue
+    int k_splits;                 // 0 / 1 = off
+    float* partial;
+    unsigned int* tile_counter;   // zero before the first launch; re-armed by the kernel
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
@@ -75,6 +80,12 @@ const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float
 const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const float* X, int ldx, float* G, int ldg,
                             int rows, int in, int out, int accumulate, float* db, int db_stride, float* W, int ldw,
                             float lr, int fuse_sgd, GemmLo lo = GemmLo());
+// Split-K for FWD / DGRAD plans whose output has fewer tiles than the chip has SMs (wide, weight-bound layers):
+// choice() returns the number of k-splits (1 = leave the plan alone); enable() rewires the plan (grid.z, ring
+// depth for two CTAs per SM).  workspace: gemm_splitk_workspace_floats() floats; counters: one zeroed uint per tile.
+int gemm_splitk_choice(const GemmPlan& plan, int num_sms);
+size_t gemm_splitk_workspace_floats(const GemmPlan& plan, int k_splits);
+const char* gemm_plan_enable_splitk(GemmPlan* plan, int k_splits, float* workspace, unsigned int* counters);
 cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 cudaError_t gemm_configure();   // opt every instantiation into > 48 KB dynamic smem (call outside graph capture)
 int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)

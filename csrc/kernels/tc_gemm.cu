@@ -30,7 +30,11 @@ static constexpr uint32_t kBlockK = 32;                 // fp32 elements = 128 B
 static constexpr uint32_t kABytes = kBlockM * 128;      // 16 KB per stage
 static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-rows x 128 B
 
-template <int MODE>
+// SPLITK (FWD / DGRAD only, wide layers with few output tiles): blockIdx.z owns a contiguous range of
+// k-blocks; every CTA writes its raw fp32 accumulator tile to a workspace and the LAST CTA to arrive at the
+// tile's counter sums the partials in split order (deterministic) and runs the fused epilogue.  Nobody
+// waits for anybody, so the CTAs of a tile need not be co-resident.
+template <int MODE, bool SPLITK = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
@@ -46,7 +50,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM;
     const int n0 = blockIdx.y * p.block_n;
-    const int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
+    int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
+    int kb0 = 0;                                           // first k-block of this CTA
+    if constexpr (SPLITK) {
+        const int per = (num_kb + p.k_splits - 1) / p.k_splits;   // host guarantees every split is non-empty
+        kb0 = (int)blockIdx.z * per;
+        num_kb = min(per, num_kb - kb0);
+    }
     const uint32_t b_bytes = p.block_n * 128u;
     const uint32_t half_bytes = kABytes + b_bytes;              // [A][B]; split mode appends [A_lo][B_lo]
     const uint32_t stage_bytes = p.split ? 2u * half_bytes : half_bytes;
@@ -97,7 +107,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                 const uint32_t a_dst = smem_base + s * stage_bytes;
                 const uint32_t b_dst = a_dst + kABytes;
-                const int k0 = kb * kBlockK;
+                const int k0 = (kb0 + kb) * kBlockK;
                 if (!A_MN) {
                     tma_load_2d(a_dst, &tmA, full_bar(s), k0, m0);
                 } else {
@@ -202,7 +212,69 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 
-        if (MODE == GEMM_FWD || MODE == GEMM_DGRAD) {
+        if constexpr (SPLITK) {
+            // ---- split-K: publish the raw partial, last arriver reduces (fixed split order) + epilogue
+            const int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+            const size_t tile_floats = (size_t)p.block_n * kBlockM;
+            float* ws = p.partial + ((size_t)tile * p.k_splits + blockIdx.z) * tile_floats;
+            for (int c = 0; c < p.block_n; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) __stcg(ws + (size_t)(c + j) * kBlockM + m_local, v[j]);   // lanes -> consecutive floats
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            volatile uint32_t* last_flag = tmem_slot_gen + 1;
+            if (warp == 2 && lane == 0) {
+                const unsigned old = atomicAdd(p.tile_counter + tile, 1u);
+                const bool last = (old == (unsigned)p.k_splits - 1u);
+                if (last) p.tile_counter[tile] = 0u;          // re-arm for the next launch (graph replay)
+                *last_flag = last ? 1u : 0u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*last_flag != 0u) {
+                __threadfence();
+                const float* wt = p.partial + (size_t)tile * p.k_splits * tile_floats;
+                float bias = 0.f;
+                if (MODE == GEMM_FWD && p.bias != nullptr && m_ok) bias = __ldg(p.bias + (size_t)m * p.bias_stride);
+                const float* __restrict__ mask = p.mask;
+                float* __restrict__ out = p.out;
+                for (int c = 0; c < p.block_n; c += 16) {
+                    float mk[16];
+                    if (MODE == GEMM_DGRAD && mask != nullptr && m_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c + j;
+                            mk[j] = (n < p.n_total) ? __ldg(mask + (size_t)n * p.ldmask + m) : 0.f;
+                        }
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    for (int sp = 0; sp < p.k_splits; ++sp) {
+                        const float* src = wt + (size_t)sp * tile_floats + (size_t)c * kBlockM + m_local;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldcg(src + (size_t)j * kBlockM);
+                    }
+                    if (!m_ok) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = v[j] + bias;
+                        if (MODE == GEMM_FWD) {
+                            if (p.relu) x = fmaxf(x, 0.f);
+                        } else if (mask != nullptr) {
+                            x = (mk[j] > 0.f) ? x : 0.f;
+                        }
+                        const int n = n0 + c + j;
+                        if (n < p.n_total) {
+                            out[(size_t)n * p.ldo + m] = x;
+                            if (p.out_lo != nullptr) p.out_lo[(size_t)n * p.ldo + m] = tf32_lo(x);
+                        }
+                    }
+                }
+            }
+        } else if (MODE == GEMM_FWD || MODE == GEMM_DGRAD) {
             float bias = 0.f;
             if (MODE == GEMM_FWD && p.bias != nullptr && m_ok) bias = __ldg(p.bias + (size_t)m * p.bias_stride);
             const float* __restrict__ mask = p.mask;
@@ -432,6 +504,46 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
     return nullptr;
 }
 
+// ---- split-K (FWD / DGRAD): more CTAs pulling on HBM when the output has fewer tiles than the chip has SMs
+int gemm_splitk_choice(const GemmPlan& plan, int num_sms) {
+    if (plan.mode == GEMM_WGRAD) return 1;
+    const GemmParams& p = plan.p;
+    const int tiles = (int)(plan.grid.x * plan.grid.y);
+    const int num_kb = (p.k_total + (int)kBlockK - 1) / (int)kBlockK;
+    if (tiles * 2 > num_sms || num_kb < 16) return 1;       // already enough CTAs, or K too short to matter
+    int splits = (2 * num_sms) / tiles;                     // aim at two resident CTAs per SM
+    if (splits > 8) splits = 8;
+    while (splits > 1 && num_kb / splits < 8) --splits;     // keep >= 8 k-blocks per CTA (pipeline fill)
+    if (splits < 2) return 1;
+    const int per = (num_kb + splits - 1) / splits;
+    return (num_kb + per - 1) / per;                        // no empty split
+}
+
+size_t gemm_splitk_workspace_floats(const GemmPlan& plan, int k_splits) {
+    return (size_t)plan.grid.x * plan.grid.y * (size_t)k_splits * (size_t)plan.p.block_n * kBlockM;
+}
+
+const char* gemm_plan_enable_splitk(GemmPlan* plan, int k_splits, float* workspace, unsigned int* counters) {
+    if (plan->mode == GEMM_WGRAD) return "split-K is implemented for FWD / DGRAD only";
+    if (k_splits < 2) return nullptr;
+    GemmParams& p = plan->p;
+    const int num_kb = (p.k_total + (int)kBlockK - 1) / (int)kBlockK;
+    const int per = (num_kb + k_splits - 1) / k_splits;
+    if ((num_kb + per - 1) / per != k_splits) return "split-K: empty split (choose k_splits with gemm_splitk_choice)";
+    if (workspace == nullptr || counters == nullptr) return "split-K needs a workspace and zeroed tile counters";
+    p.k_splits = k_splits; p.partial = workspace; p.tile_counter = counters;
+    // two CTAs per SM: at most ~100 KB of ring per CTA
+    const int stage_bytes = ((int)kABytes + p.block_n * 128) * (p.split ? 2 : 1);
+    int stages = (100 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages > per) stages = per;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    plan->smem_bytes = stages * stage_bytes + 1024 + 8 * (2 * stages + 2) + 16;
+    plan->grid.z = k_splits;
+    return nullptr;
+}
+
 static std::atomic<int> g_launches{0};
 int gemm_kernel_count() { return g_launches.load(); }
 
@@ -444,6 +556,8 @@ cudaError_t gemm_configure() {
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     g_configured = true;
     return cudaSuccess;
 }
@@ -453,6 +567,13 @@ static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
     if (!g_configured) {
         cudaError_t e = gemm_configure();
         if (e != cudaSuccess) return e;
+    }
+    if constexpr (MODE != GEMM_WGRAD) {
+        if (plan.p.k_splits > 1) {
+            tc_gemm_kernel<MODE, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return cudaGetLastError();
+        }
     }
     tc_gemm_kernel<MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
     g_launches.fetch_add(1, std::memory_order_relaxed);

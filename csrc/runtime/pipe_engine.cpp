@@ -178,6 +178,36 @@ GemmLo PipeEngine::lo_wgrad(int l, int mu) const {
     return g;
 }
 
+// Opt-in (SSB_SPLITK=1: automatic, SSB_SPLITK=k: force k where legal): give FWD / DGRAD GEMMs of wide layers
+// enough CTAs to saturate HBM (8192 outputs = only 64 tiles on 148 SMs).  Not yet the default: the kernel
+// variant still has to be validated on hardware.
+void PipeEngine::maybe_splitk(GemmPlan& g) {
+    const char* env = getenv("SSB_SPLITK");
+    if (!env || atoi(env) <= 0 || g.mode == GEMM_WGRAD) return;
+    int dev = 0, sms = 148;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int splits = gemm_splitk_choice(g, sms);
+    if (atoi(env) > 1) {
+        const int num_kb = (g.p.k_total + 31) / 32, want = atoi(env);
+        const int per = (num_kb + want - 1) / want;
+        if (per >= 1 && (num_kb + per - 1) / per == want) splits = want;
+    }
+    if (splits < 2) return;
+    const size_t ws_floats = gemm_splitk_workspace_floats(g, splits);
+    const size_t n_tiles = (size_t)g.grid.x * g.grid.y;
+    float* ws = nullptr;
+    unsigned int* counters = nullptr;
+    CUDA_CHECK(cudaMalloc(&ws, ws_floats * sizeof(float)));
+    owned_.push_back(ws);
+    CUDA_CHECK(cudaMalloc(&counters, std::max<size_t>(n_tiles, 16) * sizeof(unsigned int)));
+    CUDA_CHECK(cudaMemset(counters, 0, std::max<size_t>(n_tiles, 16) * sizeof(unsigned int)));
+    owned_.push_back(counters);
+    if (const char* err = gemm_plan_enable_splitk(&g, splits, ws, counters))
+        throw std::runtime_error(std::string("PipeEngine split-K: ") + err);
+    ++splitk_gemms_;
+}
+
 int PipeEngine::new_event() {
     cudaEvent_t e;
     CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -332,6 +362,7 @@ void PipeEngine::plan_per_mubatch() {
     }
     auto add_gemm = [&](const GemmPlan& g, int stream, int layer, int mu) {
         gemms_.push_back(g);
+        maybe_splitk(gemms_.back());
         Op op;
         op.kind = OP_GEMM; op.stream = stream; op.gemm = (int)gemms_.size() - 1; op.layer = layer; op.mu = mu;
         ops_.push_back(op);
@@ -585,6 +616,7 @@ void PipeEngine::build_coalesced() {
     auto Gl = [&](int l) { return G_ + cfg_.layers[l - 1].offset; };
     auto add_gemm = [&](const GemmPlan& g, int stream, int layer) {
         gemms_.push_back(g);
+        maybe_splitk(gemms_.back());
         Op op;
         op.kind = OP_GEMM; op.stream = stream; op.gemm = (int)gemms_.size() - 1; op.layer = layer; op.mu = -1;
         ops_.push_back(op);
@@ -1006,7 +1038,7 @@ std::string PipeEngine::describe() const {
     std::ostringstream os;
     os << "PipeEngine(stage " << cfg_.stage << "/" << cfg_.n_stages << ", layers=" << L_ << ", mb_rows=" << cfg_.mb_rows
        << ", n_mu=" << cfg_.n_mu << ", ops=" << ops_sets_[0].size() << ", kernels/step=" << kernels_per_step_
-       << ", graph_nodes=" << graph_nodes_ << ", streams=" << streams_.size() << ", events=" << events_.size() << ")";
+       << ", graph_nodes=" << graph_nodes_ << ", splitk_gemms=" << splitk_gemms_ << ", streams=" << streams_.size() << ", events=" << events_.size() << ")";
     return os.str();
 }
 

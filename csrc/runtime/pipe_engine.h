@@ -133,6 +133,7 @@ private:
     void select_set(int set);
     void finish_build();
     int new_event();
+    void maybe_splitk(GemmPlan& g);
     void emit_wait(int stream, int ev);
     int emit_record(int stream);
     void walk(int set);
@@ -186,6 +187,7 @@ private:
     std::vector<int> mu_of_;
     int64_t kernels_per_step_ = 0, graph_nodes_ = 0;
     int kernels_extra_ = 0;
+    int splitk_gemms_ = 0;
     ncclComm_t pp_comm_ = nullptr, dp_comm_ = nullptr;
     int n_mu_streams_ = 1, n_w_streams_ = 1;
     int s_comm_ = 0, s_dp_ = 0;

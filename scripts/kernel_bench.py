@@ -51,6 +51,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="default", choices=["default", "stress", "all"])
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--k-splits", type=int, default=0,
+                    help="also time the experimental split-K variant of fwd / dgrad (-1 = planner's choice, k >= 2 = force)")
     args = ap.parse_args()
     pk = peaks()
     dev = "cuda"
@@ -71,12 +74,17 @@ def main():
         dz.normal_()
         dx = K.empty_padded(rows, k, dev)
         wbytes = n * k * 4
+        pr = args.precision
         cases = {
-            "fwd": (lambda: K.linear_fwd(x, W, b, relu=True, out=y), wbytes + rows * (k + n) * 4),
-            "dgrad": (lambda: K.linear_dgrad(dz, W, mask=x, out=dx), wbytes + rows * (2 * k + n) * 4),
-            "wgrad_write": (lambda: K.linear_wgrad(dz, x, Gb[:, :k], accumulate=False, grad_b=Gb[:, k]), wbytes + rows * (k + n) * 4),
-            "wgrad_acc": (lambda: K.linear_wgrad(dz, x, Gb[:, :k], accumulate=True, grad_b=Gb[:, k]), 2 * wbytes + rows * (k + n) * 4),
+            "fwd": (lambda: K.linear_fwd(x, W, b, relu=True, out=y, precision=pr), wbytes + rows * (k + n) * 4),
+            "dgrad": (lambda: K.linear_dgrad(dz, W, mask=x, out=dx, precision=pr), wbytes + rows * (2 * k + n) * 4),
+            "wgrad_write": (lambda: K.linear_wgrad(dz, x, Gb[:, :k], accumulate=False, grad_b=Gb[:, k], precision=pr), wbytes + rows * (k + n) * 4),
+            "wgrad_acc": (lambda: K.linear_wgrad(dz, x, Gb[:, :k], accumulate=True, grad_b=Gb[:, k], precision=pr), 2 * wbytes + rows * (k + n) * 4),
         }
+        if args.k_splits:
+            ks = args.k_splits
+            cases["fwd_splitk"] = (lambda: K.linear_fwd(x, W, b, relu=True, out=y, precision=pr, k_splits=ks), cases["fwd"][1])
+            cases["dgrad_splitk"] = (lambda: K.linear_dgrad(dz, W, mask=x, out=dx, precision=pr, k_splits=ks), cases["dgrad"][1])
         for name, (fn, nbytes) in cases.items():
             warm = time_fn(fn, args.iters)
             cold = time_fn(fn, max(10, args.iters // 3), flush=flush)

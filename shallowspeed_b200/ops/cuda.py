@@ -75,26 +75,27 @@ def lo_twin(t: torch.Tensor) -> torch.Tensor:
     return lo
 
 
-def linear_fwd(x, weight, bias=None, relu=False, out=None, precision=None):
+def linear_fwd(x, weight, bias=None, relu=False, out=None, precision=None, k_splits=0):
+    """k_splits: 0 = plain kernel, -1 = planner decides, k >= 2 = force k k-splits (experimental wide-layer variant)."""
     x, weight = as_tma(x), as_tma(weight)
     rows, out_dims = x.size(0), weight.size(0)
     y = out if out is not None else empty_padded(rows, out_dims, x.device)
     b, bstride = _bias_arg(bias, out_dims)
     if _split(precision):
-        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, lo_twin(weight), lo_twin(x), None)
+        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, lo_twin(weight), lo_twin(x), None, int(k_splits))
     else:
-        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, None, None, None)
+        _C.linear_fwd(x, weight, b, bstride, bool(relu), y, None, None, None, int(k_splits))
     return y
 
 
-def linear_dgrad(dz, weight, mask=None, out=None, precision=None):
+def linear_dgrad(dz, weight, mask=None, out=None, precision=None, k_splits=0):
     dz, weight = as_tma(dz), as_tma(weight)
     dx = out if out is not None else empty_padded(dz.size(0), weight.size(1), dz.device)
     m = None if mask is None else as_tma(mask)
     if _split(precision):
-        _C.linear_dgrad(dz, weight, m, dx, lo_twin(weight), lo_twin(dz), None)
+        _C.linear_dgrad(dz, weight, m, dx, lo_twin(weight), lo_twin(dz), None, int(k_splits))
     else:
-        _C.linear_dgrad(dz, weight, m, dx, None, None, None)
+        _C.linear_dgrad(dz, weight, m, dx, None, None, None, int(k_splits))
     return dx
 
 

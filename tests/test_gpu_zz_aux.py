@@ -33,3 +33,61 @@ def test_comm_timing_mode_is_eager_and_reports_zero_without_communication(monkey
     assert tr.engine.comm_timing_enabled() and int(tr.engine.graph_nodes()) == 0
     assert tr.step(xh, yh) == ref
     assert tr.engine.comm_timing() == (0.0, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: split-K variant of the FWD / DGRAD GEMMs for wide layers (opt-in: k_splits= / SSB_SPLITK).
+# Written after the round's GPU budget was spent, so these are the first executions on hardware; they are
+# the LAST tests of the suite on purpose (a device trap here cannot poison anything that follows).
+# ---------------------------------------------------------------------------------------------------------
+EXPERIMENTAL = pytest.mark.xfail(strict=False, reason="split-K kernels: first run on hardware, opt-in code path")
+
+
+def _rand(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32).cuda()
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("precision,tol", [("tf32", 3e-3), ("fp32", 2e-5)])
+@pytest.mark.parametrize("rows,inp,out,ks", [(32, 2048, 256, -1), (8, 2048, 200, 3), (128, 4096, 128, 8), (33, 1000, 130, 2)])
+def test_splitk_forward_matches_oracle(precision, tol, rows, inp, out, ks):
+    from shallowspeed_b200.ops import cuda as K
+
+    x, w, b = _rand(rows, inp, seed=1), _rand(out, inp, seed=2) / inp ** 0.5, _rand(out, seed=3)
+    ref = torch.relu(x.double() @ w.double().T + b.double()).float()
+    plain = K.linear_fwd(x, w, b, relu=True, precision=precision)[:, :out]
+    for _ in range(2):      # second launch: the tile counters must have been re-armed
+        got = K.linear_fwd(x, w, b, relu=True, precision=precision, k_splits=ks)[:, :out]
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() <= tol * max(scale, 1.0) * 4
+        assert (got - plain).abs().max().item() <= tol * max(scale, 1.0) * 4
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("precision,tol", [("tf32", 3e-3), ("fp32", 2e-5)])
+def test_splitk_dgrad_with_relu_mask_matches_oracle(precision, tol):
+    from shallowspeed_b200.ops import cuda as K
+
+    rows, inp, out = 32, 300, 4096
+    dz, w, act = _rand(rows, out, seed=4), _rand(out, inp, seed=5) / out ** 0.5, _rand(rows, inp, seed=6)
+    ref = ((dz.double() @ w.double()) * (act > 0)).float()
+    got = K.linear_dgrad(dz, w, mask=act, precision=precision, k_splits=-1)[:, :inp]
+    assert (got - ref).abs().max().item() <= tol * max(ref.abs().max().item(), 1.0) * 4
+
+
+@EXPERIMENTAL
+def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    sizes = [784, 2048, 2048, 10]
+    x, y = synthetic_mnist(n=256)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(sizes, lr=0.05, seed_mode="index")
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
+    monkeypatch.setenv("SSB_SPLITK", "1")
+    tr = Trainer(sizes, lr=0.05, seed_mode="index")
+    assert "splitk_gemms=0" not in tr.engine.describe()
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(got, ref))
