@@ -51,6 +51,8 @@ struct GemmParams {
     int k_splits;                 // 0 / 1 = off
     float* partial;
     unsigned int* tile_counter;   // zero before the first launch; re-armed by the kernel
+    // WGRAD + fuse_sgd in fp32-equivalent mode (opt-in): also refresh the lo twin of the updated weight tile
+    float* W_lo;                  // same [out, ldw] geometry as W; nullptr = off
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)

@@ -34,7 +34,10 @@ static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-
 // k-blocks; every CTA writes its raw fp32 accumulator tile to a workspace and the LAST CTA to arrive at the
 // tile's counter sums the partials in split order (deterministic) and runs the fused epilogue.  Nobody
 // waits for anybody, so the CTAs of a tile need not be co-resident.
-template <int MODE, bool SPLITK = false>
+// WLO (WGRAD with the SGD update fused, fp32-equivalent mode): after the -lr*dW tile has been reduce-added into
+// W, the same CTA reads the updated tile back from L2 and writes its lo twin (W - trunc_tf32(W)), which removes
+// the arena-wide split kernel (and its graph edge) from the end of every step.
+template <int MODE, bool SPLITK = false, bool WLO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
@@ -345,6 +348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tma_store_commit();
                 tma_store_wait_all();
+                if constexpr (WLO) asm volatile("fence.proxy.async.global;" ::: "memory");   // async-proxy writes -> generic reads
             }
             // TMA stores clip the inner dimension at 16-byte granularity (measured on B200: with
             // in % 4 != 0 the partially valid last chunk is written in full), i.e. the bias slot in
@@ -358,6 +362,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     float* dbp = p.db + (size_t)m * p.db_stride;
                     *dbp = p.accumulate ? (*dbp + dbsum) : dbsum;
+                }
+            }
+            if constexpr (WLO) {
+                // the reduce-add retired (wait_group 0 by warp 2 lane 0, then the bar.sync above): re-read the tile
+                // through L2 (.cg) with all 128 epilogue threads, coalesced, and refresh its lo twin
+                const int t = (int)threadIdx.x - 64;
+                const int f4_per_row = p.block_n / 4;
+                for (int idx = t; idx < (int)kBlockM * f4_per_row; idx += 128) {
+                    const int r = idx / f4_per_row, c = (idx - r * f4_per_row) * 4;
+                    const int mm = m0 + r, nn = n0 + c;
+                    if (mm >= p.m_total || nn >= p.n_total) continue;
+                    const float* src = p.W + (size_t)mm * p.ldw + nn;
+                    float* dst = p.W_lo + (size_t)mm * p.ldw + nn;
+                    if (nn + 3 < p.n_total) {
+                        const float4 w = __ldcg(reinterpret_cast<const float4*>(src));
+                        *reinterpret_cast<float4*>(dst) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
+                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (nn + j < p.n_total) dst[j] = tf32_lo(__ldcg(src + j));
+                    }
                 }
             }
         }
@@ -556,6 +580,7 @@ cudaError_t gemm_configure() {
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     g_configured = true;
@@ -571,6 +596,13 @@ static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
     if constexpr (MODE != GEMM_WGRAD) {
         if (plan.p.k_splits > 1) {
             tc_gemm_kernel<MODE, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (MODE == GEMM_WGRAD) {
+        if (plan.p.W_lo != nullptr && plan.p.fuse_sgd) {
+            tc_gemm_kernel<MODE, false, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return cudaGetLastError();
         }

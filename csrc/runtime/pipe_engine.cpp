@@ -676,6 +676,9 @@ void PipeEngine::build_coalesced() {
     }
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
+    // opt-in (SSB_FUSE_WLO=1, awaiting hardware validation): the SGD-fused wgrad kernels also refresh the lo twin
+    // of the weights, so the arena-wide split kernel at the end of the step disappears
+    const bool fuse_wlo = fuse && cfg_.split && getenv("SSB_FUSE_WLO") != nullptr && atoi(getenv("SSB_FUSE_WLO")) > 0;
     int ev_bump = -1;
     if (fused_dp) {
         if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
@@ -732,6 +735,7 @@ void PipeEngine::build_coalesced() {
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
+        if (fuse_wlo) g.p.W_lo = W_lo_ + ls.offset;       // the epilogue refreshes the lo twin of its own tile
         add_gemm(g, w, l);
         if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
             const int ev_g = emit_record(w);
@@ -756,7 +760,7 @@ void PipeEngine::build_coalesced() {
     }
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
-    if (cfg_.split) {                        // weights changed: refresh their lo twin for the next step
+    if (cfg_.split && !fuse_wlo) {           // weights changed: refresh their lo twin for the next step
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);

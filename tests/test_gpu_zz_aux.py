@@ -91,3 +91,43 @@ def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
     assert "splitk_gemms=0" not in tr.engine.describe()
     got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
     assert all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(got, ref))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: SGD-fused wgrad that also refreshes the lo twin of the updated weight tile (SSB_FUSE_WLO=1).
+# ---------------------------------------------------------------------------------------------------------
+@EXPERIMENTAL
+@pytest.mark.parametrize("rows,k,n", [(32, 128, 127), (128, 784, 128), (32, 123, 10), (64, 300, 200)])
+def test_wgrad_fused_sgd_refreshes_weight_lo_twin(rows, k, n):
+    from shallowspeed_b200.ops import cuda as K
+
+    torch.manual_seed(0)
+    lr = 0.05
+    dz, x = torch.randn(rows, n, device="cuda"), torch.randn(rows, k, device="cuda")
+    ld = (k + 1 + 7) // 8 * 8
+    W, G = torch.randn(n, ld, device="cuda"), torch.zeros(n, ld, device="cuda")
+    W_ref = W.clone()
+    W_lo = torch.full((n, ld), 7.0, device="cuda")        # sentinel: every weight element must be rewritten
+    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W_ref[:, :k], lr=lr, fuse_sgd=True, precision="fp32")
+    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W[:, :k], lr=lr, fuse_sgd=True, precision="fp32",
+                   weight_lo_out=W_lo[:, :k])
+    assert torch.equal(W, W_ref)                           # the update itself is unchanged
+    assert torch.equal(W_lo[:, :k], K.lo_twin(W[:, :k]))   # lo twin of the NEW weights, bit for bit
+    assert bool((W_lo[:, k:] == 7.0).all())                # bias slot / padding untouched
+
+
+@EXPERIMENTAL
+def test_engine_fused_weight_lo_optin_is_bitwise_identical(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_FUSE_WLO", "1")
+    tr = Trainer(SIZES, lr=0.1)
+    assert int(tr.engine.kernels_per_step()) == int(base.engine.kernels_per_step()) - 1   # the split kernel is gone
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref                                      # same products, same order: identical losses
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
