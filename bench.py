@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--schedule", default="naive")
-    ap.add_argument("--comm", choices=["fused", "nccl"], default="fused")
+    ap.add_argument("--comm", choices=["fused", "nccl", "nvls"], default="fused")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--precision", choices=["fp32", "tf32"], default="fp32",
                     help="fp32 = 3xTF32 tensor-core products (fp32-equivalent, the reference's contract); tf32 = single pass")

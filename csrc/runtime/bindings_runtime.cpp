@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <nccl.h>
 
+#include "runtime/nvls_context.h"
 #include "runtime/pipe_engine.h"
 
 namespace py = pybind11;
@@ -95,6 +96,44 @@ private:
     std::unique_ptr<DpContext> ctx_;
 };
 
+// NVLS symmetric memory (multicast object shared by the DP replicas); see runtime/nvls_context.h
+class PyNvlsContext {
+public:
+    PyNvlsContext(int dp, int rank, int64_t arena_numel, double lr)
+        : ctx_(std::make_unique<NvlsContext>(dp, rank, arena_numel, (float)lr)) {}
+    static bool supported() { return NvlsContext::supported(); }
+    int export_fd() { return ctx_->export_fd(); }
+    void import_fd(int fd) { ctx_->import_fd(fd); }
+    void add_device() { ctx_->add_device(); }
+    void bind_and_map() { ctx_->bind_and_map(); }
+    torch::Tensor weights() { return blob(ctx_->weights()); }
+    torch::Tensor grads() { return blob(ctx_->grads()); }
+    int64_t bytes() { return (int64_t)ctx_->bytes(); }
+    // stand-alone collectives on the current torch stream (tests / link benchmark)
+    void all_reduce_grads() {
+        TORCH_CHECK(launch_nvls_allreduce(ctx_->params(), num_sms(), c10::cuda::getCurrentCUDAStream()) == cudaSuccess, "nvls allreduce launch");
+    }
+    void reduce_sgd() {
+        TORCH_CHECK(launch_nvls_reduce_sgd(ctx_->params(), num_sms(), c10::cuda::getCurrentCUDAStream()) == cudaSuccess, "nvls reduce_sgd launch");
+    }
+    NvlsContext* get() { return ctx_.get(); }
+
+private:
+    static int num_sms() {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return sms;
+    }
+    torch::Tensor blob(float* p) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA, dev);
+        return torch::from_blob(p, {ctx_->arena_numel()}, [](void*) {}, opts);
+    }
+    std::unique_ptr<NvlsContext> ctx_;
+};
+
 class PyEngine {
 public:
     PyEngine(const std::vector<std::tuple<int, int, int, int64_t, int>>& layers, py::dict cfg, torch::Tensor weights,
@@ -119,6 +158,7 @@ public:
     void set_pp_comm(std::shared_ptr<NcclComm> c) { pp_ = c; engine_->set_pp_comm(c->get()); }
     void set_dp_comm(std::shared_ptr<NcclComm> c) { dp_ = c; engine_->set_dp_comm(c->get()); }
     void set_dp_context(std::shared_ptr<PyDpContext> c) { dpctx_ = c; engine_->set_dp_context(c->get()); }
+    void set_nvls_context(std::shared_ptr<PyNvlsContext> c) { nvls_ = c; engine_->set_nvls_context(c->get()); }
     void build(const std::vector<std::tuple<int, int, int>>& instrs) {
         c10::cuda::CUDAGuard guard(weights_.device());
         engine_->build(instrs);
@@ -177,6 +217,7 @@ private:
     torch::Tensor weights_, grads_;
     std::shared_ptr<NcclComm> pp_, dp_;
     std::shared_ptr<PyDpContext> dpctx_;
+    std::shared_ptr<PyNvlsContext> nvls_;
     std::unique_ptr<PipeEngine> engine_;
 };
 
@@ -195,11 +236,24 @@ void bind_runtime(py::module_& m) {
         .def("open_peers", &PyDpContext::open_peers)
         .def("weights", &PyDpContext::weights)
         .def("stage_bytes", &PyDpContext::stage_bytes);
+    py::class_<PyNvlsContext, std::shared_ptr<PyNvlsContext>>(m, "NvlsContext")
+        .def(py::init<int, int, int64_t, double>())
+        .def_static("supported", &PyNvlsContext::supported)
+        .def("export_fd", &PyNvlsContext::export_fd)
+        .def("import_fd", &PyNvlsContext::import_fd)
+        .def("add_device", &PyNvlsContext::add_device)
+        .def("bind_and_map", &PyNvlsContext::bind_and_map)
+        .def("weights", &PyNvlsContext::weights)
+        .def("grads", &PyNvlsContext::grads)
+        .def("bytes", &PyNvlsContext::bytes)
+        .def("all_reduce_grads", &PyNvlsContext::all_reduce_grads)
+        .def("reduce_sgd", &PyNvlsContext::reduce_sgd);
     py::class_<PyEngine>(m, "PipeEngine")
         .def(py::init<const std::vector<std::tuple<int, int, int, int64_t, int>>&, py::dict, torch::Tensor, torch::Tensor>())
         .def("set_pp_comm", &PyEngine::set_pp_comm)
         .def("set_dp_comm", &PyEngine::set_dp_comm)
         .def("set_dp_context", &PyEngine::set_dp_context)
+        .def("set_nvls_context", &PyEngine::set_nvls_context)
         .def("build", &PyEngine::build)
         .def("stage_inputs", &PyEngine::stage_inputs)
         .def("run", &PyEngine::run)

@@ -578,7 +578,8 @@ void PipeEngine::plan_per_mubatch() {
                         if (started[ws]) { const int e = emit_record(ws); emit_wait(s_dp_, e); }
                     }
                     Op sg;
-                    sg.kind = OP_SGD; sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
+                    sg.kind = (cfg_.dp_mode == 3) ? OP_NVLS_SGD : OP_SGD;
+                    sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
                     ops_.push_back(sg);
                 }
                 break;
@@ -755,7 +756,8 @@ void PipeEngine::build_coalesced() {
             if (started[ws]) { const int e = emit_record(ws); emit_wait(s_dp_, e); }
         }
         Op sg;
-        sg.kind = OP_SGD; sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
+        sg.kind = (cfg_.dp_mode == 3) ? OP_NVLS_SGD : OP_SGD;
+        sg.stream = s_dp_; sg.a = W_; sg.b = G_; sg.scalar = cfg_.lr; sg.n = arena_numel_;
         ops_.push_back(sg);
     }
     for (size_t s = 1; s < streams_.size(); ++s)
@@ -775,7 +777,7 @@ void PipeEngine::finish_build() {
     for (auto& op : ops_sets_[0]) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
-            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT)
+            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -829,6 +831,16 @@ void PipeEngine::exec(const Op& op) {
         case OP_RELU_MASK: CUDA_CHECK(launch_relu_mask(op.a, op.lda, op.b, op.ldb, op.rows, op.cols, st, op.e)); break;
         case OP_SPLIT: CUDA_CHECK(launch_split_lo(op.a, op.b, (long)op.n, st)); break;
         case OP_SGD: CUDA_CHECK(launch_sgd(op.a, op.b, op.scalar, op.n, st)); break;
+        case OP_NVLS_SGD: {
+            if (!nvls_ctx_) throw std::runtime_error("PipeEngine: dp_mode nvls needs an NvlsContext");
+            if (nvls_ctx_->weights() != W_ || nvls_ctx_->grads() != G_)
+                throw std::runtime_error("PipeEngine: the parameter arena must live in the NVLS allocation");
+            int dev = 0, sms = 148;
+            CUDA_CHECK(cudaGetDevice(&dev));
+            CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            CUDA_CHECK(launch_nvls_reduce_sgd(nvls_ctx_->params(), sms, st));
+            break;
+        }
         case OP_ALLREDUCE:
             if (!dp_comm_) throw std::runtime_error("PipeEngine: DP all-reduce without a communicator");
             NCCL_CHECK(ncclAllReduce(op.a, op.a, (size_t)op.n, ncclFloat, ncclSum, dp_comm_, st));
@@ -861,6 +873,7 @@ static const char* op_name(int kind) {
         case OP_SOFTMAX: return "softmax";
         case OP_RELU_MASK: return "relu_mask";
         case OP_SGD: return "sgd";
+        case OP_NVLS_SGD: return "nvls_reduce_sgd";
         case OP_COMM_GROUP: return "pp_send_recv";
         case OP_ALLREDUCE: return "dp_allreduce_nccl";
         case OP_FUSED_DP: return "fused_wgrad_dp";
@@ -909,7 +922,7 @@ void PipeEngine::walk(int set) {
         if (timing) {
             if (op.kind == OP_RECORD) recorded_on[op.event] = op.stream;
             const bool comm_op = op.kind == OP_COMM_GROUP || op.kind == OP_ALLREDUCE || op.kind == OP_DP_REDUCE ||
-                                 op.kind == OP_FUSED_DP;
+                                 op.kind == OP_FUSED_DP || op.kind == OP_NVLS_SGD;
             busy = comm_op;
             bracket = comm_op || (op.kind == OP_WAIT && !is_comm_stream(op.stream) && recorded_on[op.event] >= 0 &&
                                   is_comm_stream(recorded_on[op.event]));

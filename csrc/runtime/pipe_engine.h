@@ -26,6 +26,7 @@
 
 #include "kernels/kernels.h"
 #include "runtime/dp_context.h"
+#include "runtime/nvls_context.h"
 
 struct ncclComm;
 typedef struct ncclComm* ncclComm_t;
@@ -41,7 +42,7 @@ struct LayerSpec {
 
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
-    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT
+    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT, OP_NVLS_SGD
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -76,7 +77,8 @@ struct EngineConfig {
     int training = 1;
     int use_graph = 1;
     int dp_size = 1, dp_rank = 0;
-    int dp_mode = 0;        // 0 = none/fused-sgd (dp=1), 1 = NCCL all-reduce + SGD, 2 = fused in-kernel reduction
+    int dp_mode = 0;        // 0 = none/fused-sgd (dp=1), 1 = NCCL all-reduce + SGD, 2 = fused in-kernel reduction,
+                            // 3 = NVLS: one kernel reduces the gradient arena in the switch, applies SGD, multicasts W
     int in_dim = 784, out_dim = 10;
     int split = 0;          // 1 = fp32-equivalent tensor-core products (3xTF32), 0 = single-pass TF32
 };
@@ -90,6 +92,7 @@ public:
     void set_pp_comm(ncclComm_t comm) { pp_comm_ = comm; }
     void set_dp_comm(ncclComm_t comm) { dp_comm_ = comm; }
     void set_dp_context(DpContext* ctx) { dp_ctx_ = ctx; }   // fused in-kernel DP reduction (dp_mode 2)
+    void set_nvls_context(NvlsContext* ctx) { nvls_ctx_ = ctx; }   // switch-side reduction (dp_mode 3)
 
     // instrs: (opcode, buffer_id, mubatch_id) triples from parallel.instructions.encode
     void build(const std::vector<std::tuple<int, int, int>>& instrs);
@@ -174,6 +177,7 @@ private:
     unsigned long long* chain_dbg_ = nullptr;
     int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd);
     DpContext* dp_ctx_ = nullptr;
+    NvlsContext* nvls_ctx_ = nullptr;
     std::vector<Op> ops_;
     std::vector<Op> ops_sets_[2];
     cudaGraph_t graph_sets_[2] = {nullptr, nullptr};

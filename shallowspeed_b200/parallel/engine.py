@@ -18,7 +18,7 @@ from .instructions import encode, flatten
 from .schedules import InferenceSchedule, Schedule
 from .validate import simulate
 
-DP_MODE = {"none": 0, "nccl": 1, "fused": 2}
+DP_MODE = {"none": 0, "nccl": 1, "fused": 2, "nvls": 3}
 
 
 class StepTimeout(RuntimeError):
@@ -60,6 +60,103 @@ def make_dp_context(comm: Comm, model, lr: float):
     return ctx
 
 
+# ----------------------------------------------------------------------------------------------------------
+# NVLS (switch-side reduction): the multicast object is created by the DP group's leader and reaches the other
+# replicas as a POSIX file descriptor over an AF_UNIX socket (SCM_RIGHTS) - file descriptors cannot travel
+# through torch.distributed.
+# ----------------------------------------------------------------------------------------------------------
+def serve_fd(path: str, fd: int, n_peers: int, timeout_s: float = 120.0):
+    """Leader side: hand ``fd`` to ``n_peers`` clients connecting to the unix socket ``path``."""
+    import os
+    import socket
+
+    if os.path.exists(path):
+        os.unlink(path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(max(1, n_peers))
+    srv.settimeout(timeout_s)
+    return srv
+
+
+def serve_fd_finish(srv, path: str, fd: int, n_peers: int):
+    import os
+    import socket
+
+    try:
+        for _ in range(n_peers):
+            conn, _addr = srv.accept()
+            with conn:
+                socket.send_fds(conn, [b"ssb-nvls"], [fd])
+    finally:
+        srv.close()
+        if os.path.exists(path):
+            os.unlink(path)
+
+
+def recv_fd(path: str, timeout_s: float = 120.0) -> int:
+    """Peer side: connect to the leader's socket and receive one file descriptor."""
+    import socket
+    import time
+
+    deadline = time.time() + timeout_s
+    while True:
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        try:
+            c.connect(path)
+            break
+        except (FileNotFoundError, ConnectionRefusedError):
+            c.close()
+            if time.time() > deadline:
+                raise
+            time.sleep(0.01)
+    with c:
+        c.settimeout(timeout_s)
+        msg, fds, _flags, _addr = socket.recv_fds(c, 64, 1)
+    if msg != b"ssb-nvls" or len(fds) != 1:
+        raise RuntimeError(f"NVLS fd exchange: unexpected message {msg!r} with {len(fds)} descriptors")
+    return fds[0]
+
+
+def make_nvls_context(comm: Comm, model, lr: float):
+    """Collective over the DP group: create / import the multicast object, bind this replica's memory, and move the
+    model's weight AND gradient arenas into it (the NVLS kernel reduces G through the switch and multicasts W)."""
+    assert isinstance(comm, TorchComm)
+    import os
+
+    import torch.distributed as dist
+
+    C = _C()
+    if not C.NvlsContext.supported():
+        raise RuntimeError("--comm nvls: this device / driver does not support NVLink multicast (NVLS); use --comm fused")
+    arena = model.arena
+    ctx = C.NvlsContext(comm.size, comm.rank, int(arena.weights.numel()), float(lr))
+    leader = comm.rank == 0
+    box = [None]
+    srv = fd = None
+    if leader:
+        fd = ctx.export_fd()
+        box[0] = f"/tmp/ssb_nvls_{os.getpid()}_{comm.ranks[0]}.sock"
+        srv = serve_fd(box[0], fd, comm.size - 1)       # listening BEFORE the path is announced
+    dist.broadcast_object_list(box, src=comm.ranks[0], group=comm.group)
+    if leader:
+        serve_fd_finish(srv, box[0], fd, comm.size - 1)
+        os.close(fd)
+    else:
+        got = recv_fd(box[0])
+        ctx.import_fd(got)
+        os.close(got)                                    # the imported handle keeps its own reference
+    dist.barrier(group=comm.group)
+    ctx.add_device()
+    dist.barrier(group=comm.group)                       # every device is part of the team before anyone binds
+    ctx.bind_and_map()
+    dist.barrier(group=comm.group)
+    arena.rebind(ctx.weights(), ctx.grads(), copy=True)  # parameters and gradients now live in NVLS memory
+    torch.cuda.synchronize()
+    dist.barrier(group=comm.group)
+    return ctx
+
+
 def make_nccl_comm(comm: Comm):
     """Create a native ncclComm for the ranks of a ``TorchComm`` (unique id travels over
     torch.distributed).  Returns None for size-1 communicators."""
@@ -95,6 +192,7 @@ class NativeWorker:
         # native communicators are shared between the train and the validation worker
         self.lr = optimizer.lr if optimizer is not None else 0.0
         self._dp_ctx = None
+        self._nvls_ctx = None
         if share is not None:
             self._pp_nccl, self._dp_nccl = share._pp_nccl, share._dp_nccl
         else:
@@ -103,6 +201,8 @@ class NativeWorker:
             if dp_comm is not None and self.dp_comm.Get_size() > 1:
                 if self.dp_mode == "fused":
                     self._dp_ctx = make_dp_context(self.dp_comm, model, self.lr)
+                elif self.dp_mode == "nvls":
+                    self._nvls_ctx = make_nvls_context(self.dp_comm, model, self.lr)
                 else:
                     self._dp_nccl = make_nccl_comm(self.dp_comm)
         self._engines = {}
@@ -135,6 +235,8 @@ class NativeWorker:
             eng.set_dp_comm(self._dp_nccl)
         if self._dp_ctx is not None and training:
             eng.set_dp_context(self._dp_ctx)
+        if self._nvls_ctx is not None and training:
+            eng.set_nvls_context(self._nvls_ctx)
         torch.cuda.synchronize(self.device)
         eng.build([encode(i) for i in flatten(list(sched.steps()))])
         return eng

@@ -92,3 +92,42 @@ def test_watchdog_reports_and_aborts_on_timeout(monkeypatch):
     with pytest.raises(E.StepTimeout, match="stage 1.*unhandled cuda error"):
         w.guard(FakeEngine(False), 0.01, what="step 12")
     assert w._pp_nccl.aborted
+
+
+def test_fd_passing_over_unix_socket(tmp_path):
+    """NVLS set-up hands the multicast object's POSIX fd to the other replicas with SCM_RIGHTS; check the transport
+    with a pipe: what the peers write into the received descriptors arrives at the leader's read end."""
+    import os
+
+    from shallowspeed_b200.parallel import engine as E
+
+    r, w = os.pipe()
+    path = str(tmp_path / "fd.sock")
+    srv = E.serve_fd(path, w, 2)
+    got = []
+
+    def peer(i):
+        fd = E.recv_fd(path, timeout_s=20)
+        os.write(fd, bytes([65 + i]))
+        os.close(fd)
+        got.append(i)
+
+    ts = [threading.Thread(target=peer, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    E.serve_fd_finish(srv, path, w, 2)
+    for t in ts:
+        t.join(30)
+    os.close(w)
+    assert sorted(os.read(r, 16)) == [65, 66] and sorted(got) == [0, 1]
+    os.close(r)
+    assert not os.path.exists(path)
+
+
+def test_nvls_requires_support_and_is_reported_unavailable_on_cpu():
+    from shallowspeed_b200 import _C
+
+    assert _C.NvlsContext.supported() in (False, True)
+    from shallowspeed_b200.parallel.engine import DP_MODE
+
+    assert DP_MODE["nvls"] == 3

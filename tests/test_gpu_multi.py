@@ -137,3 +137,26 @@ def test_wide_model_dp2_fused(tmp_path):
 
 def test_wide_model_dp2_pp2_1f1b(tmp_path):
     _run(2, 2, "pipedream", "fused", tmp_path, sizes=WIDE)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NVLS path (--comm nvls): the switch reduces the gradient arena and multicasts the updated weights.
+# First execution on hardware happens here (written after the round's GPU budget was spent).
+# ---------------------------------------------------------------------------------------------------------
+def _nvls_supported():
+    if not torch.cuda.is_available():
+        return False
+    from shallowspeed_b200 import _C
+
+    return bool(_C.NvlsContext.supported())
+
+
+NVLS_EXPERIMENTAL = pytest.mark.xfail(strict=False, reason="NVLS path: first run on hardware, opt-in code path")
+
+
+@NVLS_EXPERIMENTAL
+@pytest.mark.parametrize("dp,pp,sched,coalesce", [(2, 1, "naive", True), (2, 1, "gpipe", False), (2, 2, "pipedream", True)])
+def test_nvls_reduce_sgd_matches_oracle(dp, pp, sched, coalesce, tmp_path):
+    if not _nvls_supported():
+        pytest.skip("NVLink multicast not supported on this device / driver")
+    _run(dp, pp, sched, "nvls", tmp_path, coalesce=coalesce)

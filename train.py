@@ -86,7 +86,7 @@ def build_parser():
     p.add_argument("--device", choices=["auto", "cpu", "cuda"], default="auto")
     p.add_argument("--engine", choices=["auto", "python", "native"], default="auto",
                    help="python = portable instruction VM; native = C++ executor + sm_100a kernels")
-    p.add_argument("--comm", choices=["fused", "nccl"], default="fused",
+    p.add_argument("--comm", choices=["fused", "nccl", "nvls"], default="fused",
                    help="native engine DP path: in-kernel reduction over peer memory, or plain NCCL all-reduce (A/B baseline)")
     p.add_argument("--no-graph", action="store_true", help="native engine: do not capture the step in a CUDA graph")
     p.add_argument("--precision", choices=["tf32", "fp32"], default="fp32",
