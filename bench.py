@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--schedule", default="naive")
     ap.add_argument("--comm", choices=["fused", "nccl", "nvls"], default="fused")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the informational single-GPU tf32-mode measurement")
     ap.add_argument("--precision", choices=["fp32", "tf32"], default="fp32",
                     help="fp32 = 3xTF32 tensor-core products (fp32-equivalent, the reference's contract); tf32 = single pass")
     ap.add_argument("--pp", type=int, default=1, help="pipeline stages (dp = gpus / pp)")
@@ -212,6 +213,34 @@ def run_ours(args):
         comm = {"exposed_ms_per_step": max_over_ranks(exposed_ms, dev), "busy_ms_per_step": max_over_ranks(busy_ms, dev),
                 "note": "eager (no CUDA graph) diagnostic run; throughput numbers of this run are not bench values"}
 
+    # Informational: the same workload with single-pass TF32 products (`--precision tf32`), single GPU only.  It never
+    # replaces the headline (fp32-equivalent) number and can never take the bench down with it.
+    alt = None
+    if world == 1 and args.precision == "fp32" and not args.no_alt:
+        try:
+            t2 = Trainer(sizes, global_batch_size=gbs, n_mubatches=args.n_mubatches, lr=LR, schedule=args.schedule,
+                         use_graph=not args.no_graph, device=dev, seed_mode=args.seed_mode, precision="tf32")
+            s2 = torch.cuda.ExternalStream(t2.engine.main_stream(), device=dev)
+
+            def alt_step(i):
+                j = i % pool
+                t2.step_async(x_dev[j], y_dev[j])
+
+            for i in range(args.warmup):
+                alt_step(i)
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(s2)
+            for i in range(args.steps):
+                alt_step(args.warmup + i)
+            a1.record(s2)
+            torch.cuda.synchronize(dev)
+            ms_alt = a0.elapsed_time(a1)
+            alt = {"precision": "tf32 (single-pass tf32 products, fp32 accumulate)", "value": args.steps * gbs / (ms_alt * 1e-3),
+                   "unit": "samples/s", "ms_per_step": ms_alt / args.steps, "note": "informational; the headline value is the fp32-equivalent mode"}
+        except Exception as exc:   # noqa: BLE001 - informational only
+            alt = {"error": str(exc)[:200]}
+
     if dp > 1:   # replicas must still be bit-identical after the run
         from shallowspeed_b200.utils import assert_sync, get_model_hash
 
@@ -233,6 +262,7 @@ def run_ours(args):
             "gpu_launches": kps * args.steps,
             "clocks": clocks,
             **({"comm": comm} if comm is not None else {}),
+            **({"tf32_mode": alt} if alt is not None else {}),
             "config": {"model": "MLP " + "-".join(str(v) for v in (sizes if len(sizes) <= 9 else sizes[:2] + ["..."] + sizes[-2:])),
                        "global_batch": gbs, "per_replica_batch": local_bs,
                        "n_mubatches": args.n_mubatches, "seq_len": None,
