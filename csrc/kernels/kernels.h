@@ -170,17 +170,18 @@ struct ChainParams {
     int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
-    int dbg_flags;                   // experiments: 1 = skip global stores, 2 = skip smem stores (fwd epilogue)
+    int mc_base;                     // > 0 (multicast variant only): index of the quarter-tile forward weight maps
     unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only
 };
 struct ChainPlan {
     ChainParams p;
     CUtensorMap* maps_dev;
     int grid, smem_bytes;
+    int cluster;                     // 1, or 4: micro-batch CTAs share the weight stream through TMA multicast
 };
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split = false);
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       const float* W_lo = nullptr, const float* x_lo = nullptr);
+                       const float* W_lo = nullptr, const float* x_lo = nullptr, bool multicast = false);
 void chain_plan_free(ChainPlan* plan);
 cudaError_t chain_configure();
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream);

@@ -55,8 +55,34 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define DBG(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = gtime(); } while (0)
 
-// SPLIT (3xTF32) is a compile-time switch: the single-pass TF32 instantiation carries none of the lo-twin code
-template <bool SPLIT>
+// ---- cluster helpers (MC variant only)
+__device__ __forceinline__ uint32_t chain_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void chain_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same smem offset (and signals the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
+// SPLIT (3xTF32) is a compile-time switch: the single-pass TF32 instantiation carries none of the lo-twin code.
+// MC (opt-in, SSB_CHAIN_MC=1): the 4 micro-batch CTAs form a cluster and share the weight stream - CTA r fetches a
+// quarter of every weight tile and multicasts it to all four, so each SM issues 4x fewer L2 requests for the same
+// operand bytes; a ring slot is released only when all four MMA warps have retired their reads of it.
+template <bool SPLIT, bool MC = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -91,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), MC ? 4 : 1);             // MC: the slot is rewritten by all four producers
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(act_ready_bar, 8);                         // one arrive per epilogue warp
@@ -105,6 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    uint32_t crank = 0;
+    if constexpr (MC) {
+        crank = chain_cluster_rank();
+        chain_cluster_sync();                                // every peer's barriers exist before anyone multicasts
+    }
 
     // number of backward GEMMs: layers L..lo (layer 1's dgrad is skipped on the first stage)
     const int bwd_lo = p.first_stage ? 2 : 1;
@@ -133,10 +164,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             DBG(0, it);
                             mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (SPLIT ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
+                                if constexpr (MC) {      // my quarter (32 of the 128 weight rows) of the tile, to all four CTAs
+                                    tma_load_2d_mc(a_dst + j * kABytes + crank * kPanelBytes, p.maps + p.mc_base + (l - 1), full_bar(s),
+                                                   (kb0 + j) * kBlockK, (int)crank * 32, (uint16_t)0xF);
+                                } else
                                 tma_load_2d(a_dst + j * kABytes, p.maps + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                 if (with_x)
                                     tma_load_2d(a_dst + stage_b_off + j * b_bytes, p.maps + 2 * L, full_bar(s), (kb0 + j) * kBlockK, row0);
                                 if (SPLIT) {
+                                    if constexpr (MC) {
+                                        tma_load_2d_mc(a_dst + half_stage + j * kABytes + crank * kPanelBytes, p.maps + p.mc_base + L + (l - 1),
+                                                       full_bar(s), (kb0 + j) * kBlockK, (int)crank * 32, (uint16_t)0xF);
+                                    } else
                                     tma_load_2d(a_dst + half_stage + j * kABytes, p.maps + lo_base + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                     if (with_x)
                                         tma_load_2d(a_dst + half_stage + stage_b_off + j * b_bytes, p.maps + lo_base + 2 * L, full_bar(s),
@@ -158,7 +197,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         if (elect_one()) {
                             DBG(0, it);
                             mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (SPLIT ? 2u : 1u));
-                            for (int j = 0; j < cnt; ++j)
+                            for (int j = 0; j < cnt; ++j) {
+                                if constexpr (MC) {      // panel `crank` of the four [32 k x 32 m] panels, to all four CTAs
+                                    tma_load_2d_mc(a_dst + j * kABytes + crank * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s),
+                                                   32 * (int)crank, (kb0 + j) * kBlockK, (uint16_t)0xF);
+                                    if (SPLIT)
+                                        tma_load_2d_mc(a_dst + half_stage + j * kABytes + crank * kPanelBytes,
+                                                       p.maps + lo_base + 2 * (l - 1) + 1, full_bar(s), 32 * (int)crank, (kb0 + j) * kBlockK,
+                                                       (uint16_t)0xF);
+                                } else {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     tma_load_2d(a_dst + j * kABytes + i * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s), 32 * i,
@@ -167,6 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                         tma_load_2d(a_dst + half_stage + j * kABytes + i * kPanelBytes, p.maps + lo_base + 2 * (l - 1) + 1,
                                                     full_bar(s), 32 * i, (kb0 + j) * kBlockK);
                                 }
+                                }
+                            }
                         }
                         __syncwarp();
                     }
@@ -218,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
                                           ((kb0 + j) | k4) != 0 ? 1u : 0u);
                         }
-                        umma_commit(empty_bar(s));
+                        if constexpr (MC) umma_commit_mc(empty_bar(s), (uint16_t)0xF);   // frees the slot in all four CTAs
+                        else umma_commit(empty_bar(s));
                         if (kb0 + cnt >= nkb) umma_commit(tmem_full_bar);
                     }
                     __syncwarp();
@@ -499,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+    if constexpr (MC) chain_cluster_sync();                  // peers may still signal my ring barriers until they are done too
 }
 
 // =========================================================================== host side
@@ -526,7 +577,7 @@ bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out
 }
 
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       const float* W_lo, const float* x_lo) {
+                       const float* W_lo, const float* x_lo, bool multicast) {
     *plan = ChainPlan{};
     ChainParams& p = plan->p;
     p = params;
@@ -534,7 +585,18 @@ const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* 
     p.n_pad = (p.mb_rows + 15) / 16 * 16;
     p.split = (W_lo != nullptr) ? 1 : 0;
     const int nmaps = 2 * L + 1;
-    std::vector<CUtensorMap> host(nmaps * (p.split ? 2 : 1));
+    // multicast variant: clusters of 4 micro-batch CTAs; needs quarter-tile (32-row) maps of the forward weights
+    const bool mc = multicast && n_mubatches >= 4 && n_mubatches % 4 == 0;
+    p.mc_base = mc ? nmaps * (p.split ? 2 : 1) : 0;
+    plan->cluster = mc ? 4 : 1;
+    std::vector<CUtensorMap> host(nmaps * (p.split ? 2 : 1) + (mc ? L * (p.split ? 2 : 1) : 0));
+    if (mc)
+        for (int half = 0; half < (p.split ? 2 : 1); ++half)
+            for (int l = 0; l < L; ++l) {
+                const ChainLayer& ly = p.layers[l];
+                if (const char* e = make_tmap_k(&host[p.mc_base + half * L + l], (half ? W_lo : p.W) + ly.w_off, ly.in, ly.out, ly.ldw, 32))
+                    return e;
+            }
     for (int half = 0; half < (p.split ? 2 : 1); ++half) {
         const float* Wb = half ? W_lo : p.W;
         const float* xb = half ? x_lo : x;
@@ -581,10 +643,25 @@ void chain_plan_free(ChainPlan* plan) {
 cudaError_t chain_configure() {
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
+    if (plan.cluster > 1) {                                  // multicast variant: clusters of 4 micro-batch CTAs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(plan.grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = plan.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = plan.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (plan.p.split) return cudaLaunchKernelEx(&cfg, mlp_chain_kernel<true, true>, plan.p);
+        return cudaLaunchKernelEx(&cfg, mlp_chain_kernel<false, true>, plan.p);
+    }
     if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     else mlp_chain_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     return cudaGetLastError();

@@ -251,7 +251,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.inv_batch = 1.0f / (float)cfg_.global_batch;
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
-    cp.dbg_flags = getenv("SSB_CHAIN_FLAGS") ? atoi(getenv("SSB_CHAIN_FLAGS")) : 0;
+    cp.mc_base = 0;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {
             CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
@@ -261,8 +261,10 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
         cp.dbg = chain_dbg_;
     }
     ChainPlan plan;
+    // opt-in (SSB_CHAIN_MC=1, awaiting hardware validation): clusters of 4 micro-batch CTAs multicast the weight tiles
+    const bool mc = getenv("SSB_CHAIN_MC") != nullptr && atoi(getenv("SSB_CHAIN_MC")) > 0;
     const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, cfg_.split ? W_lo_ : nullptr,
-                                 cfg_.split ? act_lo_all_[0] : nullptr);
+                                 cfg_.split ? act_lo_all_[0] : nullptr, mc);
     if (err) throw std::runtime_error(std::string("PipeEngine chain plan: ") + err);
     chain_plans_.push_back(plan);
     Op op;

@@ -1,0 +1,126 @@
+"""Opt-in kernels written after the round's GPU budget was spent (split-K GEMMs, lo-twin-refreshing wgrad, multicast
+chain kernel).  NOT collected by default (file name): tests/test_gpu_zz_aux.py runs each group in its OWN python process,
+so a device trap in one experimental kernel cannot poison the CUDA context of anything else.
+
+    python -m pytest tests/experimental_cases.py -q            # run them directly on a GPU box
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: split-K variant of the FWD / DGRAD GEMMs for wide layers (opt-in: k_splits= / SSB_SPLITK).
+# Written after the round's GPU budget was spent, so these are the first executions on hardware;
+# each group runs in its own process (tests/test_gpu_zz_aux.py).
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _rand(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32).cuda()
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 3e-3), ("fp32", 2e-5)])
+@pytest.mark.parametrize("rows,inp,out,ks", [(32, 2048, 256, -1), (8, 2048, 200, 3), (128, 4096, 128, 8), (33, 1000, 130, 2)])
+def test_splitk_forward_matches_oracle(precision, tol, rows, inp, out, ks):
+    from shallowspeed_b200.ops import cuda as K
+
+    x, w, b = _rand(rows, inp, seed=1), _rand(out, inp, seed=2) / inp ** 0.5, _rand(out, seed=3)
+    ref = torch.relu(x.double() @ w.double().T + b.double()).float()
+    plain = K.linear_fwd(x, w, b, relu=True, precision=precision)[:, :out]
+    for _ in range(2):      # second launch: the tile counters must have been re-armed
+        got = K.linear_fwd(x, w, b, relu=True, precision=precision, k_splits=ks)[:, :out]
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() <= tol * max(scale, 1.0) * 4
+        assert (got - plain).abs().max().item() <= tol * max(scale, 1.0) * 4
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 3e-3), ("fp32", 2e-5)])
+def test_splitk_dgrad_with_relu_mask_matches_oracle(precision, tol):
+    from shallowspeed_b200.ops import cuda as K
+
+    rows, inp, out = 32, 300, 4096
+    dz, w, act = _rand(rows, out, seed=4), _rand(out, inp, seed=5) / out ** 0.5, _rand(rows, inp, seed=6)
+    ref = ((dz.double() @ w.double()) * (act > 0)).float()
+    got = K.linear_dgrad(dz, w, mask=act, precision=precision, k_splits=-1)[:, :inp]
+    assert (got - ref).abs().max().item() <= tol * max(ref.abs().max().item(), 1.0) * 4
+
+
+def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    sizes = [784, 2048, 2048, 10]
+    x, y = synthetic_mnist(n=256)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(sizes, lr=0.05, seed_mode="index")
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
+    monkeypatch.setenv("SSB_SPLITK", "1")
+    tr = Trainer(sizes, lr=0.05, seed_mode="index")
+    assert "splitk_gemms=0" not in tr.engine.describe()
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(got, ref))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: SGD-fused wgrad that also refreshes the lo twin of the updated weight tile (SSB_FUSE_WLO=1).
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,k,n", [(32, 128, 127), (128, 784, 128), (32, 123, 10), (64, 300, 200)])
+def test_wgrad_fused_sgd_refreshes_weight_lo_twin(rows, k, n):
+    from shallowspeed_b200.ops import cuda as K
+
+    torch.manual_seed(0)
+    lr = 0.05
+    dz, x = torch.randn(rows, n, device="cuda"), torch.randn(rows, k, device="cuda")
+    ld = (k + 1 + 7) // 8 * 8
+    W, G = torch.randn(n, ld, device="cuda"), torch.zeros(n, ld, device="cuda")
+    W_ref = W.clone()
+    W_lo = torch.full((n, ld), 7.0, device="cuda")        # sentinel: every weight element must be rewritten
+    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W_ref[:, :k], lr=lr, fuse_sgd=True, precision="fp32")
+    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W[:, :k], lr=lr, fuse_sgd=True, precision="fp32",
+                   weight_lo_out=W_lo[:, :k])
+    assert torch.equal(W, W_ref)                           # the update itself is unchanged
+    assert torch.equal(W_lo[:, :k], K.lo_twin(W[:, :k]))   # lo twin of the NEW weights, bit for bit
+    assert bool((W_lo[:, k:] == 7.0).all())                # bias slot / padding untouched
+
+
+def test_engine_fused_weight_lo_optin_is_bitwise_identical(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_FUSE_WLO", "1")
+    tr = Trainer(SIZES, lr=0.1)
+    assert int(tr.engine.kernels_per_step()) == int(base.engine.kernels_per_step()) - 1   # the split kernel is gone
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref                                      # same products, same order: identical losses
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: chain kernel with a 4-CTA cluster sharing the weight stream through TMA multicast (SSB_CHAIN_MC=1).
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("n_mu", [4, 8])
+def test_chain_multicast_cluster_is_bitwise_identical(monkeypatch, precision, n_mu):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 3)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision=precision)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(3)]
+    monkeypatch.setenv("SSB_CHAIN_MC", "1")
+    tr = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision=precision)
+    assert tr.engine.uses_chain()
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(3)]
+    assert got == ref                                      # same MMAs in the same order: identical losses
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
+
