@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--schedule", default="naive")
     ap.add_argument("--comm", choices=["fused", "nccl", "nvls"], default="fused")
+    ap.add_argument("--pp-transport", choices=["nccl", "peer"], default=None)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the informational single-GPU tf32-mode measurement")
     ap.add_argument("--precision", choices=["fp32", "tf32"], default="fp32",
@@ -149,7 +150,7 @@ def run_ours(args):
     trainer = Trainer(sizes, global_batch_size=gbs, n_mubatches=args.n_mubatches, lr=LR, schedule=args.schedule,
                       dp_comm=dp_comm if dp > 1 else None, pp_comm=pp_comm if args.pp > 1 else None, grid=grid,
                       comm_mode=args.comm, use_graph=not args.no_graph, device=dev, seed_mode=args.seed_mode,
-                      precision=args.precision)
+                      precision=args.precision, pp_transport=args.pp_transport)
     eng = trainer.engine
 
     # input pools: this replica's shard of `pool` distinct global batches
@@ -267,7 +268,8 @@ def run_ours(args):
                        "global_batch": gbs, "per_replica_batch": local_bs,
                        "n_mubatches": args.n_mubatches, "seq_len": None,
                        "parallelism": f"dp{dp}" + (f"xpp{args.pp}" if args.pp > 1 else ""), "schedule": args.schedule,
-                       "dp_comm": args.comm if dp > 1 else "none", "cuda_graph": (not args.no_graph) and comm is None,
+                       "dp_comm": args.comm if dp > 1 else "none",
+                       "pp_transport": (trainer.worker.pp_transport if args.pp > 1 else "none"), "cuda_graph": (not args.no_graph) and comm is None,
                        "kernels_per_step": kps, "graph_nodes": int(eng.graph_nodes()),
                        "l2": f"inputs cycle through a pool of {pool} distinct batches ({pool * h2d / 1e6:.0f} MB > 126 MB L2); "
                              "the 0.7 MB of weights are legitimately L2-resident across steps",

@@ -134,6 +134,20 @@ private:
     std::unique_ptr<NvlsContext> ctx_;
 };
 
+// Peer-memory pipeline transport (runtime/pp_context.h)
+class PyPpContext {
+public:
+    PyPpContext(int n_mu, int mb_rows, int ld_in, int ld_out, bool is_first, bool is_last)
+        : ctx_(std::make_unique<PpContext>(n_mu, mb_rows, ld_in, ld_out, is_first, is_last)) {}
+    py::bytes export_handles() { return py::bytes(ctx_->export_handles()); }
+    void open_prev(const std::string& h) { ctx_->open_prev(h); }
+    void open_next(const std::string& h) { ctx_->open_next(h); }
+    PpContext* get() { return ctx_.get(); }
+
+private:
+    std::unique_ptr<PpContext> ctx_;
+};
+
 class PyEngine {
 public:
     PyEngine(const std::vector<std::tuple<int, int, int, int64_t, int>>& layers, py::dict cfg, torch::Tensor weights,
@@ -159,6 +173,8 @@ public:
     void set_dp_comm(std::shared_ptr<NcclComm> c) { dp_ = c; engine_->set_dp_comm(c->get()); }
     void set_dp_context(std::shared_ptr<PyDpContext> c) { dpctx_ = c; engine_->set_dp_context(c->get()); }
     void set_nvls_context(std::shared_ptr<PyNvlsContext> c) { nvls_ = c; engine_->set_nvls_context(c->get()); }
+    void set_pp_context(std::shared_ptr<PyPpContext> c) { ppctx_ = c; engine_->set_pp_context(c->get()); }
+    std::pair<int, int> boundary_lds() { return {engine_->act_ld(0), engine_->act_ld((int)engine_->config().layers.size())}; }
     void build(const std::vector<std::tuple<int, int, int>>& instrs) {
         c10::cuda::CUDAGuard guard(weights_.device());
         engine_->build(instrs);
@@ -218,6 +234,7 @@ private:
     std::shared_ptr<NcclComm> pp_, dp_;
     std::shared_ptr<PyDpContext> dpctx_;
     std::shared_ptr<PyNvlsContext> nvls_;
+    std::shared_ptr<PyPpContext> ppctx_;
     std::unique_ptr<PipeEngine> engine_;
 };
 
@@ -248,12 +265,19 @@ void bind_runtime(py::module_& m) {
         .def("bytes", &PyNvlsContext::bytes)
         .def("all_reduce_grads", &PyNvlsContext::all_reduce_grads)
         .def("reduce_sgd", &PyNvlsContext::reduce_sgd);
+    py::class_<PyPpContext, std::shared_ptr<PyPpContext>>(m, "PpContext")
+        .def(py::init<int, int, int, int, bool, bool>())
+        .def("export_handles", &PyPpContext::export_handles)
+        .def("open_prev", &PyPpContext::open_prev)
+        .def("open_next", &PyPpContext::open_next);
     py::class_<PyEngine>(m, "PipeEngine")
         .def(py::init<const std::vector<std::tuple<int, int, int, int64_t, int>>&, py::dict, torch::Tensor, torch::Tensor>())
         .def("set_pp_comm", &PyEngine::set_pp_comm)
         .def("set_dp_comm", &PyEngine::set_dp_comm)
         .def("set_dp_context", &PyEngine::set_dp_context)
         .def("set_nvls_context", &PyEngine::set_nvls_context)
+        .def("set_pp_context", &PyEngine::set_pp_context)
+        .def("boundary_lds", &PyEngine::boundary_lds)
         .def("build", &PyEngine::build)
         .def("stage_inputs", &PyEngine::stage_inputs)
         .def("run", &PyEngine::run)

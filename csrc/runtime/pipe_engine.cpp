@@ -314,6 +314,17 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         chain_ok_ = L_ >= 1 && L_ <= kChainMaxLayers && !getenv("SSB_NO_CHAIN") &&
                     chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0, cfg_.split != 0);
     }
+    if (pp_ctx_) {
+        // peer-memory transport: the neighbours write straight into my receive slots, which therefore live in the
+        // IPC-shared PpContext (one set of slots; reuse across steps is protected by the credit flags)
+        if (pp_ctx_->n_mu() != M || pp_ctx_->mb_rows() != cfg_.mb_rows || pp_ctx_->ld_in() != act_ld_[0] || pp_ctx_->ld_out() != act_ld_[L_])
+            throw std::runtime_error("PipeEngine: PpContext geometry does not match this stage");
+        if (!cfg_.is_first) x_stage_sets_[0] = x_stage_sets_[1] = pp_ctx_->act_in();
+        if (!cfg_.is_last && cfg_.training) {
+            dz_all_[L_] = pp_ctx_->dz_in();
+            for (int mu = 0; mu < M; ++mu) dz_[mu][L_] = dz_all_[L_] + (size_t)mu * cfg_.mb_rows * act_ld_[L_];
+        }
+    }
     instrs_ = instrs;
     mu_of_ = mu_of;
     // Two complete plans, one per input-staging buffer: step i reads staging set i % 2 while the copy
@@ -362,6 +373,11 @@ void PipeEngine::plan_per_mubatch() {
         ops_.insert(ops_.begin(), be);   // before the 'begin' event every stream forks from
         ++kernels_extra_;
     }
+    if (pp_ctx_) {
+        Op be;
+        be.kind = OP_PP_BUMP; be.stream = 0;
+        ops_.insert(ops_.begin(), be);   // step counter of the boundary flags, before every stream forks
+    }
     auto add_gemm = [&](const GemmPlan& g, int stream, int layer, int mu) {
         gemms_.push_back(g);
         maybe_splitk(gemms_.back());
@@ -376,6 +392,51 @@ void PipeEngine::plan_per_mubatch() {
     for (int i = 0; i < n;) {
         const int opc = std::get<0>(instrs[i]);
         // ------------------------------------------------ communication group
+        if (pp_ctx_ && opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
+            // ---- peer-memory transport: pushes first (one-sided: they never wait for the peer's schedule position,
+            // only for the credit of the previous step), then the waits for what this group receives
+            use(s_comm_);
+            std::vector<std::pair<int, int>> recvs;  // (mu, is_act)
+            std::vector<Op> waits;
+            int j = i;
+            for (; j < n; ++j) {
+                const int o = std::get<0>(instrs[j]);
+                if (!(o >= I_RECV_ACT && o <= I_SEND_GRAD)) break;
+                const int mu = mu_of[j];
+                Op x;
+                x.stream = s_comm_; x.mu = mu;
+                if (o == I_SEND_ACT) {
+                    if (ev_fwd[mu] >= 0) emit_wait(s_comm_, ev_fwd[mu]);
+                    x.kind = OP_PP_PUSH; x.a = act_[mu][L_]; x.b = pp_ctx_->next_act_in(mu); x.n = (int64_t)mb * act_ld_[L_];
+                    x.c = reinterpret_cast<float*>(pp_ctx_->next_act_arrived(mu));
+                    x.d = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->act_credit()));
+                    if (!x.b) throw std::runtime_error("PipeEngine: SendActivations without a successor mapping");
+                    ops_.push_back(x);
+                } else if (o == I_SEND_GRAD) {
+                    if (ev_bwd[mu] >= 0) emit_wait(s_comm_, ev_bwd[mu]);
+                    x.kind = OP_PP_PUSH; x.a = dz_[mu][0]; x.b = pp_ctx_->prev_dz_in(mu); x.n = (int64_t)mb * act_ld_[0];
+                    x.c = reinterpret_cast<float*>(pp_ctx_->prev_dz_arrived(mu));
+                    x.d = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->dz_credit()));
+                    if (!x.b) throw std::runtime_error("PipeEngine: SendInputGrad without a predecessor mapping");
+                    ops_.push_back(x);
+                } else if (o == I_RECV_ACT) {
+                    x.kind = OP_PP_WAIT; x.a = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->act_arrived(mu)));
+                    waits.push_back(x);
+                    recvs.push_back({mu, 1});
+                } else {
+                    x.kind = OP_PP_WAIT; x.a = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->dz_arrived(mu)));
+                    waits.push_back(x);
+                    recvs.push_back({mu, 0});
+                }
+            }
+            for (auto& w : waits) ops_.push_back(w);
+            if (!recvs.empty()) {
+                const int ev = emit_record(s_comm_);
+                for (auto& r : recvs) (r.second ? ev_in : ev_gout)[r.first] = ev;
+            }
+            i = j;
+            continue;
+        }
         if (opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
             Op grp;
             grp.kind = OP_COMM_GROUP; grp.stream = s_comm_;
@@ -594,6 +655,13 @@ void PipeEngine::plan_per_mubatch() {
     // ---- join every side stream back into the main stream
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
+    if (pp_ctx_) {                           // everything that read my receive slots is done: hand them back
+        Op cr;
+        cr.kind = OP_PP_CREDIT; cr.stream = 0;
+        cr.a = reinterpret_cast<float*>(pp_ctx_->prev_act_credit());
+        cr.b = cfg_.training ? reinterpret_cast<float*>(pp_ctx_->next_dz_credit()) : nullptr;
+        ops_.push_back(cr);
+    }
     if (cfg_.split && cfg_.training) {       // weights changed: refresh their lo twin for the next step
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
@@ -779,7 +847,8 @@ void PipeEngine::finish_build() {
     for (auto& op : ops_sets_[0]) {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
-            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD)
+            op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD ||
+            op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT || op.kind == OP_PP_CREDIT || op.kind == OP_PP_BUMP)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -861,6 +930,15 @@ void PipeEngine::exec(const Op& op) {
         case OP_FUSED_DP: CUDA_CHECK(launch_fused_wgrad_dp(dp_plans_[op.gemm], st)); break;
         case OP_DP_REDUCE: CUDA_CHECK(launch_dp_reduce_sgd(dp_plans_[op.gemm], st)); break;
         case OP_BUMP_EPOCH: CUDA_CHECK(launch_bump_epoch(dp_ctx_->epoch_ptr(), st)); break;
+        case OP_PP_BUMP: CUDA_CHECK(launch_bump_epoch(pp_ctx_->epoch_ptr(), st)); break;
+        case OP_PP_PUSH:
+            CUDA_CHECK(launch_pp_push(op.a, op.b, op.n, reinterpret_cast<uint32_t*>(op.c), reinterpret_cast<const uint32_t*>(op.d),
+                                      pp_ctx_->epoch_ptr(), pp_ctx_->push_done_ptr(), st));
+            break;
+        case OP_PP_WAIT: CUDA_CHECK(launch_pp_wait(reinterpret_cast<const uint32_t*>(op.a), pp_ctx_->epoch_ptr(), st)); break;
+        case OP_PP_CREDIT:
+            CUDA_CHECK(launch_pp_credit(reinterpret_cast<uint32_t*>(op.a), reinterpret_cast<uint32_t*>(op.b), pp_ctx_->epoch_ptr(), st));
+            break;
         case OP_MEMCPY_LOSS:
             CUDA_CHECK(cudaMemcpyAsync(op.a, loss_dev_, sizeof(float) * cfg_.n_mu, cudaMemcpyDeviceToHost, st));
             break;
@@ -881,6 +959,10 @@ static const char* op_name(int kind) {
         case OP_FUSED_DP: return "fused_wgrad_dp";
         case OP_DP_REDUCE: return "dp_reduce_sgd";
         case OP_BUMP_EPOCH: return "bump_epoch";
+        case OP_PP_BUMP: return "pp_bump_epoch";
+        case OP_PP_PUSH: return "pp_push";
+        case OP_PP_WAIT: return "pp_wait";
+        case OP_PP_CREDIT: return "pp_credit";
         case OP_CHAIN: return "mlp_chain";
         case OP_SPLIT: return "split_lo";
         case OP_MEMCPY_LOSS: return "loss_d2h";
@@ -924,7 +1006,7 @@ void PipeEngine::walk(int set) {
         if (timing) {
             if (op.kind == OP_RECORD) recorded_on[op.event] = op.stream;
             const bool comm_op = op.kind == OP_COMM_GROUP || op.kind == OP_ALLREDUCE || op.kind == OP_DP_REDUCE ||
-                                 op.kind == OP_FUSED_DP || op.kind == OP_NVLS_SGD;
+                                 op.kind == OP_FUSED_DP || op.kind == OP_NVLS_SGD || op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT;
             busy = comm_op;
             bracket = comm_op || (op.kind == OP_WAIT && !is_comm_stream(op.stream) && recorded_on[op.event] >= 0 &&
                                   is_comm_stream(recorded_on[op.event]));

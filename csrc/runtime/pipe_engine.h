@@ -27,6 +27,7 @@
 #include "kernels/kernels.h"
 #include "runtime/dp_context.h"
 #include "runtime/nvls_context.h"
+#include "runtime/pp_context.h"
 
 struct ncclComm;
 typedef struct ncclComm* ncclComm_t;
@@ -42,7 +43,8 @@ struct LayerSpec {
 
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
-    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT, OP_NVLS_SGD
+    OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT, OP_NVLS_SGD,
+    OP_PP_PUSH, OP_PP_WAIT, OP_PP_CREDIT, OP_PP_BUMP
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -93,6 +95,7 @@ public:
     void set_dp_comm(ncclComm_t comm) { dp_comm_ = comm; }
     void set_dp_context(DpContext* ctx) { dp_ctx_ = ctx; }   // fused in-kernel DP reduction (dp_mode 2)
     void set_nvls_context(NvlsContext* ctx) { nvls_ctx_ = ctx; }   // switch-side reduction (dp_mode 3)
+    void set_pp_context(PpContext* ctx) { pp_ctx_ = ctx; }         // pipeline boundaries over peer memory instead of NCCL p2p
 
     // instrs: (opcode, buffer_id, mubatch_id) triples from parallel.instructions.encode
     void build(const std::vector<std::tuple<int, int, int>>& instrs);
@@ -178,6 +181,7 @@ private:
     int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd);
     DpContext* dp_ctx_ = nullptr;
     NvlsContext* nvls_ctx_ = nullptr;
+    PpContext* pp_ctx_ = nullptr;
     std::vector<Op> ops_;
     std::vector<Op> ops_sets_[2];
     cudaGraph_t graph_sets_[2] = {nullptr, nullptr};

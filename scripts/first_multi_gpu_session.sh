@@ -11,6 +11,13 @@ mkdir -p "$OUT"
 echo "== 1. NVLS tests (xfail markers ignored)"
 timeout 600 python -m pytest tests/test_gpu_multi.py -k nvls -q --runxfail -x 2>&1 | tail -30 | tee "$OUT/nvls_tests.log"
 
+echo "== 1b. peer-memory pipeline transport tests + pp=2 bench (nccl vs peer)"
+timeout 600 python -m pytest tests/test_gpu_multi.py -k "pp_peer" -q --runxfail -x 2>&1 | tail -30 | tee "$OUT/pp_peer_tests.log"
+for tr in nccl peer; do
+    timeout 300 python bench.py --gpus "$N" --pp "$N" --schedule gpipe --n-mubatches 8 --pp-transport "$tr" --steps 200 --warmup 30 2>/dev/null \
+        | tail -1 | tee -a "$OUT/bench_pp_transports.jsonl"
+done
+
 echo "== 2. switch all-reduce vs NCCL"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29731 \
     scripts/nvls_bench.py 2>&1 | grep '^{' | tee "$OUT/nvls_bench.jsonl"

@@ -157,6 +157,29 @@ def make_nvls_context(comm: Comm, model, lr: float):
     return ctx
 
 
+def make_pp_context(comm: Comm, eng, n_mu: int, mb_rows: int, is_first: bool, is_last: bool):
+    """Collective over the pipeline group: receive slots + flags of this stage in IPC-shared memory, mapped by the two
+    neighbours (peer-memory boundary transport, ``--pp-transport peer``)."""
+    assert isinstance(comm, TorchComm)
+    import torch.distributed as dist
+
+    ld_in, ld_out = eng.boundary_lds()
+    ctx = _C().PpContext(int(n_mu), int(mb_rows), int(ld_in), int(ld_out), bool(is_first), bool(is_last))
+    blobs = [None] * comm.size
+    dist.all_gather_object(blobs, (bytes(ctx.export_handles()), int(ld_in), int(ld_out)), group=comm.group)
+    if not is_first:
+        h, _pin, pout = blobs[comm.rank - 1]
+        assert pout == ld_in, f"stage boundary mismatch: predecessor writes rows of {pout} floats, this stage reads {ld_in}"
+        ctx.open_prev(h)
+    if not is_last:
+        h, nin, _nout = blobs[comm.rank + 1]
+        assert nin == ld_out, f"stage boundary mismatch: successor reads rows of {nin} floats, this stage writes {ld_out}"
+        ctx.open_next(h)
+    torch.cuda.synchronize()
+    dist.barrier(group=comm.group)
+    return ctx
+
+
 def make_nccl_comm(comm: Comm):
     """Create a native ncclComm for the ranks of a ``TorchComm`` (unique id travels over
     torch.distributed).  Returns None for size-1 communicators."""
@@ -175,7 +198,7 @@ def make_nccl_comm(comm: Comm):
 class NativeWorker:
     def __init__(self, dp_comm, pp_comm, model, dataset, optimizer, grid: Optional[ProcessGrid] = None,
                  comm_mode: str = "fused", use_graph: bool = True, precision: str = "fp32", share=None,
-                 validate_schedules: bool = True):
+                 validate_schedules: bool = True, pp_transport: Optional[str] = None):
         self.dp_comm = dp_comm if dp_comm is not None else SelfComm()
         self.pp_comm = pp_comm if pp_comm is not None else SelfComm()
         self.stage_id = self.pp_comm.Get_rank()
@@ -183,6 +206,11 @@ class NativeWorker:
         self.model, self.dataset, self.optimizer = model, dataset, optimizer
         self.use_graph, self.precision = use_graph, precision
         self.validate_schedules = validate_schedules
+        import os as _os
+
+        # pipeline boundaries: NCCL send/recv (default) or one-sided pushes into the neighbour's memory (opt-in)
+        self.pp_transport = pp_transport or ("peer" if _os.environ.get("SSB_PP_PEER", "0") not in ("", "0") else "nccl")
+        assert self.pp_transport in ("nccl", "peer")
         self.device = model.arena.weights.device
         assert self.device.type == "cuda", "NativeWorker needs the model on a CUDA device (model.to('cuda'))"
         if self.dp_comm.Get_size() == 1:
@@ -237,6 +265,9 @@ class NativeWorker:
             eng.set_dp_context(self._dp_ctx)
         if self._nvls_ctx is not None and training:
             eng.set_nvls_context(self._nvls_ctx)
+        if self.pp_transport == "peer" and self.pipeline_depth > 1:
+            eng.set_pp_context(make_pp_context(self.pp_comm, eng, sched.num_micro_batches, self.dataset.mubatch_size,
+                                               sched.is_first_stage, sched.is_last_stage))
         torch.cuda.synchronize(self.device)
         eng.build([encode(i) for i in flatten(list(sched.steps()))])
         return eng
@@ -322,7 +353,7 @@ class Trainer:
 
     def __init__(self, layer_sizes, global_batch_size=128, n_mubatches=4, lr=0.006, schedule="naive",
                  dp_comm=None, pp_comm=None, grid: Optional[ProcessGrid] = None, comm_mode="fused",
-                 use_graph=True, device=None, seed_mode="shape", precision="fp32", watchdog_s=None):
+                 use_graph=True, device=None, seed_mode="shape", precision="fp32", watchdog_s=None, pp_transport=None):
         from ..models.mlp import MLP
         from ..optimizer import SGD
         from .schedules import SCHEDULE_NAME_TO_CLS
@@ -340,7 +371,7 @@ class Trainer:
             mubatch_size = self.local_batch_size // n_mubatches
 
         self.worker = NativeWorker(dp_comm, pp_comm, self.model, _Shape(), self.optimizer, grid=grid,
-                                   comm_mode=comm_mode, use_graph=use_graph, precision=precision)
+                                   comm_mode=comm_mode, use_graph=use_graph, precision=precision, pp_transport=pp_transport)
         cls = SCHEDULE_NAME_TO_CLS[schedule] if isinstance(schedule, str) else schedule
         self.schedule = cls(n_mubatches, pp, self.pp_comm.Get_rank())
         self.engine = self.worker.engine_for(self.schedule)

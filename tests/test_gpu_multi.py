@@ -13,8 +13,9 @@ WIDE = [784, 1024, 1000, 1024, 520, 1024, 130, 10]     # > 128 wide: per-layer G
 GBS, N_MU, LR, STEPS = 128, 4, 0.05, 4
 
 
-def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce, two_shot=False, sizes=None):
+def _worker(rank, world, dp, pp, sched_name, comm_mode, port, out_dir, coalesce, two_shot=False, sizes=None, extra_env=None):
     sizes = sizes or SIZES
+    os.environ.update(extra_env or {})
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     if not coalesce:
@@ -74,14 +75,15 @@ def _cpu_oracle(sizes=None):
     return [p.data.clone() for p in model.parameters()], MLP(sizes, 0, 1, GBS)
 
 
-def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True, two_shot=False, sizes=None):
+def _run(dp, pp, sched, comm_mode, tmp_path, coalesce=True, two_shot=False, sizes=None, extra_env=None):
     import torch.multiprocessing as mp
 
     world = dp * pp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29800 + (os.getpid() + dp * 7 + pp * 13 + len(sched)) % 150
-    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce, two_shot, sizes), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, dp, pp, sched, comm_mode, port, str(tmp_path), coalesce, two_shot, sizes, extra_env), nprocs=world,
+             join=True)
     got = [p for s in range(pp) for p in torch.load(tmp_path / f"stage{s}.pt")["params"]]
     ref, init = _cpu_oracle(sizes)
     for p0, a, b in zip(init.parameters(), got, ref):
@@ -160,3 +162,16 @@ def test_nvls_reduce_sgd_matches_oracle(dp, pp, sched, coalesce, tmp_path):
     if not _nvls_supported():
         pytest.skip("NVLink multicast not supported on this device / driver")
     _run(dp, pp, sched, "nvls", tmp_path, coalesce=coalesce)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Peer-memory pipeline transport (--pp-transport peer / SSB_PP_PEER=1): one-sided pushes + epoch flags instead of
+# NCCL send/recv.  First execution on hardware happens here.
+# ---------------------------------------------------------------------------------------------------------
+PP_PEER_EXPERIMENTAL = pytest.mark.xfail(strict=False, reason="peer-memory pipeline transport: first run on hardware, opt-in code path")
+
+
+@PP_PEER_EXPERIMENTAL
+@pytest.mark.parametrize("dp,pp,sched", [(1, 2, "naive"), (1, 2, "gpipe"), (1, 2, "pipedream"), (1, 4, "gpipe"), (2, 2, "pipedream")])
+def test_pp_peer_transport_matches_oracle(dp, pp, sched, tmp_path):
+    _run(dp, pp, sched, "fused", tmp_path, extra_env={"SSB_PP_PEER": "1"})

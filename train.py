@@ -88,6 +88,9 @@ def build_parser():
                    help="python = portable instruction VM; native = C++ executor + sm_100a kernels")
     p.add_argument("--comm", choices=["fused", "nccl", "nvls"], default="fused",
                    help="native engine DP path: in-kernel reduction over peer memory, or plain NCCL all-reduce (A/B baseline)")
+    p.add_argument("--pp-transport", choices=["nccl", "peer"], default=None,
+                   help="native engine, stage boundaries: NCCL send/recv (default) or one-sided pushes into the neighbour's "
+                        "memory over NVLink with epoch flags (opt-in)")
     p.add_argument("--no-graph", action="store_true", help="native engine: do not capture the step in a CUDA graph")
     p.add_argument("--precision", choices=["tf32", "fp32"], default="fp32",
                    help="tensor-core math: fp32 = 3xTF32 split (fp32-equivalent, the reference's contract); tf32 = single pass")
@@ -178,9 +181,10 @@ def main(args):
         from shallowspeed_b200.parallel.engine import NativeWorker
 
         worker = NativeWorker(dp_comm, pp_comm, model, dataset, optimizer, grid=grid, comm_mode=args.comm,
-                              use_graph=not args.no_graph, precision=args.precision)
+                              use_graph=not args.no_graph, precision=args.precision, pp_transport=args.pp_transport)
         val_worker = NativeWorker(None, pp_comm, model, val_dataset, None, grid=grid, comm_mode="nccl",
-                                  use_graph=not args.no_graph, precision=args.precision, share=worker)
+                                  use_graph=not args.no_graph, precision=args.precision, share=worker,
+                                  pp_transport=args.pp_transport)
     else:
         worker = Worker(dp_comm, pp_comm, model, dataset, optimizer, device=device)
         val_worker = Worker(None, pp_comm, model, val_dataset, None, device=device)
