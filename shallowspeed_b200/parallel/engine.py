@@ -152,7 +152,8 @@ def make_nvls_context(comm: Comm, model, lr: float):
     ctx.bind_and_map()
     dist.barrier(group=comm.group)
     arena.rebind(ctx.weights(), ctx.grads(), copy=True)  # parameters and gradients now live in NVLS memory
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     dist.barrier(group=comm.group)
     return ctx
 
@@ -175,7 +176,8 @@ def make_pp_context(comm: Comm, eng, n_mu: int, mb_rows: int, is_first: bool, is
         h, nin, _nout = blobs[comm.rank + 1]
         assert nin == ld_out, f"stage boundary mismatch: successor reads rows of {nin} floats, this stage writes {ld_out}"
         ctx.open_next(h)
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     dist.barrier(group=comm.group)
     return ctx
 
