@@ -227,6 +227,7 @@ public:
     bool coalesced() { return engine_->coalesced(); }
     int64_t main_stream() { return reinterpret_cast<int64_t>(engine_->main_stream()); }
     std::string describe() { return engine_->describe(); }
+    std::string plan_text(int set) { return engine_->plan_text(set); }
     std::vector<unsigned long long> chain_timeline() { return engine_->chain_timeline(); }
 
 private:
@@ -299,6 +300,7 @@ void bind_runtime(py::module_& m) {
         .def("coalesced", &PyEngine::coalesced)
         .def("main_stream", &PyEngine::main_stream)
         .def("describe", &PyEngine::describe)
+        .def("plan_text", &PyEngine::plan_text, py::arg("set") = 0)
         .def("chain_timeline", &PyEngine::chain_timeline);
 }
 

@@ -1135,6 +1135,27 @@ std::vector<unsigned long long> PipeEngine::chain_timeline() {
     return v;
 }
 
+// One line per lowered op of staging set `set`: "<index> <op> stream=<s> [event=<e>] [layer=<l>] [mu=<m>]" - the plan a
+// step replays, for debugging and for the plan self-check in the tests.
+std::string PipeEngine::plan_text(int set) const {
+    std::ostringstream os;
+    const auto& ops = ops_sets_[set & 1];
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& op = ops[i];
+        os << i << " " << op_name(op.kind) << " stream=" << op.stream;
+        if (op.event >= 0) os << " event=" << op.event;
+        if (op.layer >= 0) os << " layer=" << op.layer;
+        if (op.mu >= 0) os << " mu=" << op.mu;
+        if (op.kind == OP_COMM_GROUP) {
+            os << " [";
+            for (const auto& it : op.comm) os << (it.is_send ? "send->" : "recv<-") << it.peer << ":" << it.count << " ";
+            os << "]";
+        }
+        os << "\n";
+    }
+    return os.str();
+}
+
 std::string PipeEngine::describe() const {
     std::ostringstream os;
     os << "PipeEngine(stage " << cfg_.stage << "/" << cfg_.n_stages << ", layers=" << L_ << ", mb_rows=" << cfg_.mb_rows

@@ -130,6 +130,7 @@ public:
     cudaStream_t main_stream() { return streams_[0]; }
     const EngineConfig& config() const { return cfg_; }
     std::string describe() const;
+    std::string plan_text(int set = 0) const;
     std::vector<unsigned long long> chain_timeline();   // SSB_CHAIN_TIMELINE=1: globaltimer stamps of the chain kernel
 
 private:

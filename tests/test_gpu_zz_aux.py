@@ -35,6 +35,21 @@ def test_comm_timing_mode_is_eager_and_reports_zero_without_communication(monkey
     assert tr.engine.comm_timing() == (0.0, 0.0)
 
 
+
+@pytest.mark.parametrize("env", [{}, {"SSB_NO_COALESCE": "1"}, {"SSB_NO_CHAIN": "1"}, {"SSB_NO_CHAIN": "1", "SSB_NO_COALESCE": "1"}])
+def test_lowered_plans_pass_the_self_check(monkeypatch, env):
+    """Every wait refers to an earlier record, no event is recorded twice, every side stream is forked and joined."""
+    from shallowspeed_b200.parallel.engine import Trainer
+    from shallowspeed_b200.parallel.plan_check import check_plan
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    tr = Trainer(SIZES, lr=0.1)
+    for s in (0, 1):
+        stats = check_plan(tr.engine.plan_text(s))
+        assert stats["kernels_and_copies"] >= 3 and stats["ops"] == len(tr.engine.plan_text(s).splitlines())
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Experimental opt-in kernels (tests/experimental_cases.py): one isolated python process per group, so a device
 # trap in a kernel that has never run on hardware cannot poison this process.  Non-strict xfail: the outcome is
