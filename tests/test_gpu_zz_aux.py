@@ -65,6 +65,6 @@ def test_experimental_group_in_isolated_process(group):
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "experimental_cases.py"), "-k", group, "-q", "-x",
-                        "-p", "no:cacheprovider"], cwd=root, capture_output=True, text=True, timeout=900)
+                        "-p", "no:cacheprovider"], cwd=root, capture_output=True, text=True, timeout=300)
     tail = (r.stdout or "")[-3000:] + (r.stderr or "")[-1500:]
     assert r.returncode == 0, tail
