@@ -19,6 +19,23 @@ SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
 # ---------------------------------------------------------------------------------------------------------
 
 
+def _report(got, ref, tol):
+    """One-glance description of a mismatch (these kernels get few GPU runs: make each one count)."""
+    err = (got.double() - ref.double()).abs()
+    bad = err > tol
+    if not bool(bad.any()):
+        return "ok"
+    rows = bad.any(1).nonzero().flatten()
+    cols = bad.any(0).nonzero().flatten()
+    r0, c0 = int(rows[0]), int(cols[0])
+    nz = bad & (ref != 0)
+    ratio = (got.double()[nz] / ref.double()[nz]).median().item() if bool(nz.any()) else float("nan")
+    return (f"max err {err.max().item():.3e} (tol {tol:.1e}); {int(bad.sum())}/{bad.numel()} wrong; rows {int(rows[0])}..{int(rows[-1])} "
+            f"({len(rows)} of {got.size(0)}), cols {int(cols[0])}..{int(cols[-1])} ({len(cols)} of {got.size(1)}); "
+            f"first bad [{r0},{c0}]: got {got[r0, c0].item():.6g} ref {ref[r0, c0].item():.6g}; median got/ref over bad = {ratio:.4g}; "
+            f"zeros in got: {int((got == 0).sum())}, nan: {int(torch.isnan(got).sum())}")
+
+
 def _rand(*shape, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return torch.randn(*shape, generator=g, dtype=torch.float32).cuda()
@@ -34,9 +51,9 @@ def test_splitk_forward_matches_oracle(precision, tol, rows, inp, out, ks):
     plain = K.linear_fwd(x, w, b, relu=True, precision=precision)[:, :out]
     for _ in range(2):      # second launch: the tile counters must have been re-armed
         got = K.linear_fwd(x, w, b, relu=True, precision=precision, k_splits=ks)[:, :out]
-        scale = ref.abs().max().item()
-        assert (got - ref).abs().max().item() <= tol * max(scale, 1.0) * 4
-        assert (got - plain).abs().max().item() <= tol * max(scale, 1.0) * 4
+        bound = tol * max(ref.abs().max().item(), 1.0) * 4
+        assert (got - ref).abs().max().item() <= bound, "vs oracle: " + _report(got, ref, bound)
+        assert (got - plain).abs().max().item() <= bound, "vs plain kernel: " + _report(got, plain, bound)
 
 
 @pytest.mark.parametrize("precision,tol", [("tf32", 3e-3), ("fp32", 2e-5)])
@@ -47,7 +64,8 @@ def test_splitk_dgrad_with_relu_mask_matches_oracle(precision, tol):
     dz, w, act = _rand(rows, out, seed=4), _rand(out, inp, seed=5) / out ** 0.5, _rand(rows, inp, seed=6)
     ref = ((dz.double() @ w.double()) * (act > 0)).float()
     got = K.linear_dgrad(dz, w, mask=act, precision=precision, k_splits=-1)[:, :inp]
-    assert (got - ref).abs().max().item() <= tol * max(ref.abs().max().item(), 1.0) * 4
+    bound = tol * max(ref.abs().max().item(), 1.0) * 4
+    assert (got - ref).abs().max().item() <= bound, _report(got, ref, bound)
 
 
 def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
@@ -79,12 +97,15 @@ def test_wgrad_fused_sgd_refreshes_weight_lo_twin(rows, k, n):
     ld = (k + 1 + 7) // 8 * 8
     W, G = torch.randn(n, ld, device="cuda"), torch.zeros(n, ld, device="cuda")
     W_ref = W.clone()
+    stale = K.lo_twin(W.clone()[:, :k])                    # lo twin of the OLD weights: what a stale read-back would produce
     W_lo = torch.full((n, ld), 7.0, device="cuda")        # sentinel: every weight element must be rewritten
     K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W_ref[:, :k], lr=lr, fuse_sgd=True, precision="fp32")
     K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W[:, :k], lr=lr, fuse_sgd=True, precision="fp32",
                    weight_lo_out=W_lo[:, :k])
-    assert torch.equal(W, W_ref)                           # the update itself is unchanged
-    assert torch.equal(W_lo[:, :k], K.lo_twin(W[:, :k]))   # lo twin of the NEW weights, bit for bit
+    assert torch.equal(W, W_ref), "update changed: " + _report(W, W_ref, 0.0)
+    want = K.lo_twin(W[:, :k])
+    assert torch.equal(W_lo[:, :k], want), ("lo twin of the NEW weights, bit for bit: " + _report(W_lo[:, :k], want, 0.0) +
+                                            f"; sentinel survivors {int((W_lo[:, :k] == 7.0).sum())}; equals stale twin: {torch.equal(W_lo[:, :k], stale)}")
     assert bool((W_lo[:, k:] == 7.0).all())                # bias slot / padding untouched
 
 
