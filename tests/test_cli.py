@@ -50,3 +50,25 @@ def test_bench_reference_arm_json_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 5 and d["value"] > 0
     assert d["config"]["global_batch"] == 128 and d["config"]["n_mubatches"] == 4
+
+
+def test_parsers_know_the_runtime_knobs():
+    sys.path.insert(0, ROOT)
+    try:
+        import bench
+        import train
+    finally:
+        sys.path.remove(ROOT)
+    a = train.build_parser().parse_args(["--dp", "2", "--pp", "2", "--schedule", "pipedream-flush", "--comm", "nvls",
+                                         "--pp-transport", "peer", "--watchdog-s", "30", "--precision", "tf32"])
+    assert (a.comm, a.pp_transport, a.watchdog_s, a.precision, a.schedule) == ("nvls", "peer", 30.0, "tf32", "pipedream-flush")
+    d = train.build_parser().parse_args([])
+    assert (d.dp, d.pp, d.schedule, d.comm, d.pp_transport, d.watchdog_s, d.precision) == (1, 1, "naive", "fused", None, None, "fp32")
+    old = sys.argv
+    try:
+        sys.argv = ["bench.py"]
+        b = bench.parse()
+    finally:
+        sys.argv = old
+    assert b.gpus == 1 and b.impl in ("ours", None, "") or b.impl == "ours"
+    assert b.precision == "fp32" and b.comm == "fused" and b.pp_transport is None and not b.no_alt
