@@ -195,5 +195,25 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_", &sgd_);
     m.def("argmax_correct", &argmax_correct);
     m.def("gemm_kernel_count", &ssb::gemm_kernel_count);
+    // host-only planning logic, callable without a GPU (tests/test_splitk_planning.py):
+    // (k_splits chosen, k-blocks per split, error string of enable() with dummy buffers or "")
+    m.def("splitk_plan", [](int m_total, int n_rows, int k_total, int num_sms, int force) {
+        ssb::GemmPlan plan{};
+        plan.mode = ssb::GEMM_FWD;
+        plan.p.m_total = m_total; plan.p.n_total = n_rows; plan.p.k_total = k_total;
+        plan.p.block_n = n_rows >= 256 ? 256 : (n_rows + 15) / 16 * 16;
+        plan.grid = dim3((m_total + 127) / 128, (n_rows + plan.p.block_n - 1) / plan.p.block_n, 1);
+        int splits = force > 0 ? force : ssb::gemm_splitk_choice(plan, num_sms);
+        const int num_kb = (k_total + 31) / 32;
+        std::string err;
+        if (splits > 1) {
+            float dummy_ws;
+            unsigned int dummy_ctr;
+            const char* e = ssb::gemm_plan_enable_splitk(&plan, splits, &dummy_ws, &dummy_ctr);
+            if (e) err = e;
+        }
+        const int per = splits > 0 ? (num_kb + splits - 1) / splits : num_kb;
+        return std::make_tuple(splits, per, (int)plan.grid.z, plan.p.stages, plan.smem_bytes, err);
+    });
     ssb::bind_runtime(m);
 }
