@@ -1,5 +1,6 @@
 // Python bindings (torch extension) for the sm_100a kernels and the native runtime.
 #include <torch/extension.h>
+#include <pybind11/stl.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
@@ -195,6 +196,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_", &sgd_);
     m.def("argmax_correct", &argmax_correct);
     m.def("gemm_kernel_count", &ssb::gemm_kernel_count);
+    m.def("chain_budget", [](int mb_rows, bool split) {
+        int kps = 0, stages = 0, smem = 0;
+        const bool ok = ssb::chain_budget(mb_rows, split, &kps, &stages, &smem);
+        return std::make_tuple(ok, kps, stages, smem);
+    });
+    m.def("chain_eligible", [](const std::vector<std::pair<int, int>>& in_out, int mb_rows, int out_dim, bool has_loss, bool split) {
+        std::vector<ssb::ChainLayer> ls(in_out.size());
+        for (size_t i = 0; i < in_out.size(); ++i) { ls[i] = ssb::ChainLayer{}; ls[i].in = in_out[i].first; ls[i].out = in_out[i].second; }
+        return ssb::chain_eligible(ls.data(), (int)ls.size(), mb_rows, out_dim, has_loss, split);
+    });
+    m.def("dp_layer_geometry", [](int in, int out, int dp, bool one_shot) {
+        int block_n = 0, tm = 0, tn = 0;
+        int64_t slots = 0, slot_floats = 0;
+        ssb::dp_layer_geometry(in, out, dp, &block_n, &tm, &tn, &slots, &slot_floats, one_shot ? 1 : 0);
+        return std::make_tuple(block_n, tm, tn, slots, slot_floats);
+    });
     // host-only planning logic, callable without a GPU (tests/test_splitk_planning.py):
     // (k_splits chosen, k-blocks per split, error string of enable() with dummy buffers or "")
     m.def("splitk_plan", [](int m_total, int n_rows, int k_total, int num_sms, int force) {

@@ -182,6 +182,7 @@ struct ChainPlan {
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split = false);
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
                        const float* W_lo = nullptr, const float* x_lo = nullptr, bool multicast = false);
+bool chain_budget(int mb_rows, bool split, int* kps, int* stages, int* smem_bytes);   // host arithmetic only
 void chain_plan_free(ChainPlan* plan);
 cudaError_t chain_configure();
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream);

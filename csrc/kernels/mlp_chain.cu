@@ -556,13 +556,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
 const char* make_tmap_mn(CUtensorMap* map, const float* base, int inner, int outer, int ld);                 // tc_gemm.cu
 const char* make_tmap_k(CUtensorMap* map, const float* base, int inner, int outer, int ld, int box_outer);   // tc_gemm.cu
 
-static bool chain_smem_fits(int mb_rows, bool split) {
+// Shared-memory plan of the chain kernel for one micro-batch size: k-panels per ring stage, ring depth, total bytes.
+// Pure host arithmetic (no CUDA calls) so it can be unit-tested without a GPU (tests/test_planning.py).
+bool chain_budget(int mb_rows, bool split, int* kps_out, int* stages_out, int* smem_bytes_out) {
     const int n_pad = (mb_rows + 15) / 16 * 16;
     const int abuf_bytes = 4 * n_pad * 128;
     const int scratch_bytes = n_pad * kScratchLd * 4 + 256;
     const int budget = 222 * 1024 - (split ? 4 : 2) * abuf_bytes - scratch_bytes;
-    const int stage_bytes = ((int)kABytes + n_pad * 128) * (split ? 2 : 1);      // kps = 1
-    return budget / stage_bytes >= 2;
+    int kps = 4, stage_bytes = 0, stages = 0;
+    for (; kps >= 1; kps >>= 1) {            // biggest stage (fewest waits/commits) that still double-buffers
+        stage_bytes = kps * ((int)kABytes + n_pad * 128) * (split ? 2 : 1);
+        stages = budget / stage_bytes;
+        if (stages >= 2) break;
+    }
+    if (kps < 1 || stages < 2) return false;
+    if (stages > 8) stages = 8;
+    *kps_out = kps;
+    *stages_out = stages;
+    *smem_bytes_out = stages * stage_bytes + (split ? 4 : 2) * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
+    return true;
+}
+
+static bool chain_smem_fits(int mb_rows, bool split) {
+    int kps, stages, smem;
+    return chain_budget(mb_rows, split, &kps, &stages, &smem);
 }
 
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split) {
@@ -617,20 +634,11 @@ const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* 
         return "chain_plan: tensor map upload failed";
     plan->maps_dev = dev;
     p.maps = dev;
-    const int abuf_bytes = 4 * p.n_pad * 128;
-    const int scratch_bytes = p.n_pad * kScratchLd * 4 + 256;
-    const int budget = 222 * 1024 - (p.split ? 4 : 2) * abuf_bytes - scratch_bytes;
-    int kps = 4, stage_bytes = 0, stages = 0;
-    for (; kps >= 1; kps >>= 1) {            // biggest stage (fewest waits/commits) that still double-buffers
-        stage_bytes = kps * ((int)kABytes + p.n_pad * 128) * (p.split ? 2 : 1);
-        stages = budget / stage_bytes;
-        if (stages >= 2) break;
-    }
-    if (kps < 1 || stages < 2) return "chain_plan: shared memory budget too small";
-    if (stages > 8) stages = 8;
+    int kps = 0, stages = 0, smem = 0;
+    if (!chain_budget(p.mb_rows, p.split != 0, &kps, &stages, &smem)) return "chain_plan: shared memory budget too small";
     p.kps = kps;
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + (p.split ? 4 : 2) * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
+    plan->smem_bytes = smem;
     plan->grid = n_mubatches;
     return nullptr;
 }
