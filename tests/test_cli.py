@@ -72,3 +72,32 @@ def test_parsers_know_the_runtime_knobs():
         sys.argv = old
     assert b.gpus == 1 and b.impl in ("ours", None, "") or b.impl == "ours"
     assert b.precision == "fp32" and b.comm == "fused" and b.pp_transport is None and not b.no_alt
+
+
+def test_tuning_file_ships_with_every_variant_off_and_env_wins(tmp_path, monkeypatch):
+    import json
+
+    import shallowspeed_b200 as pkg
+
+    cfg = json.load(open(os.path.join(ROOT, "shallowspeed_b200", "tuning.json")))
+    assert all(v is False for k, v in cfg.items() if k.startswith("SSB_")), "flip a switch only together with its measurement"
+    assert pkg.TUNING == {} or all(k in os.environ for k in pkg.TUNING)
+    # semantics of the loader, on a scratch copy
+    import importlib.util
+
+    src = open(os.path.join(ROOT, "shallowspeed_b200", "__init__.py")).read().split("TUNING = _apply_tuning()")[0]
+    scratch = tmp_path / "pkgcopy"
+    scratch.mkdir()
+    (scratch / "__init__.py").write_text(src.replace("from . import", "# from . import"))
+    (scratch / "tuning.json").write_text(json.dumps({"SSB_CHAIN_MC": True, "SSB_SPLITK": 4, "SSB_FUSE_WLO": False, "other": 1}))
+    monkeypatch.delenv("SSB_CHAIN_MC", raising=False)
+    monkeypatch.setenv("SSB_SPLITK", "2")
+    monkeypatch.delenv("SSB_FUSE_WLO", raising=False)
+    spec = importlib.util.spec_from_file_location("pkgcopy", scratch / "__init__.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    applied = mod._apply_tuning()
+    try:
+        assert applied == {"SSB_CHAIN_MC": "1", "SSB_SPLITK": "2"} and "SSB_FUSE_WLO" not in os.environ
+    finally:
+        os.environ.pop("SSB_CHAIN_MC", None)        # set by the loader itself, not by monkeypatch
