@@ -93,6 +93,9 @@ void PipeEngine::alloc_buffers() {
     y_stage_ = y_stage_sets_[0];
     loss_dev_ = dalloc(std::max(M, 16));
     CUDA_CHECK(cudaMallocHost(&loss_host_, 2 * sizeof(float) * std::max(M, 16)));   // one slot per staging set
+    // opt-in (SSB_LOSS_ZEROCOPY=1, awaiting hardware validation): the loss head stores its per-micro-batch losses straight
+    // into this pinned, device-mapped host buffer (16 bytes over PCIe), which drops the D2H copy node from the step
+    loss_zero_copy_ = getenv("SSB_LOSS_ZEROCOPY") != nullptr && atoi(getenv("SSB_LOSS_ZEROCOPY")) > 0;
     for (int i = 0; i < 2 * std::max(M, 16); ++i) loss_host_[i] = 0.f;
     {
         int* p = nullptr;
@@ -208,6 +211,11 @@ void PipeEngine::maybe_splitk(GemmPlan& g) {
     ++splitk_gemms_;
 }
 
+// where the loss values of the plan being built go: device scratch (then a D2H copy), or directly the host slot
+float* PipeEngine::loss_target() const {
+    return loss_zero_copy_ ? loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16) : loss_dev_;
+}
+
 int PipeEngine::new_event() {
     cudaEvent_t e;
     CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -246,7 +254,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     }
     cp.target = y_stage_; cp.ldt = y_ld_;
     cp.probs = probs_all_; cp.ldp = act_ld_[L_];
-    cp.loss = loss_dev_;
+    cp.loss = loss_target();
     cp.mb_rows = cfg_.mb_rows; cp.mu_base = mu_base;
     cp.inv_batch = 1.0f / (float)cfg_.global_batch;
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
@@ -567,6 +575,7 @@ void PipeEngine::plan_per_mubatch() {
                         lh.d = dz_[mu][L_]; lh.ldd = act_ld_[L_];
                         lh.rows = mb; lh.cols = cfg_.out_dim; lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = mu;
                     lh.e = cfg_.split ? dz_lo_[mu][L_] : nullptr;
+                        lh.f = loss_zero_copy_ ? loss_target() : nullptr;
                         ops_.push_back(lh);
                     } else if (L_ > 0 && cfg_.layers[L_ - 1].relu) {
                         Op rm;
@@ -667,7 +676,7 @@ void PipeEngine::plan_per_mubatch() {
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
     }
-    if (cfg_.training && last) {
+    if (cfg_.training && last && !loss_zero_copy_) {
         Op cp;
         cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
         ops_.push_back(cp);
@@ -743,6 +752,7 @@ void PipeEngine::build_coalesced() {
         lh.d = dz_all_[L_]; lh.ldd = act_ld_[L_]; lh.rows = rows; lh.cols = cfg_.out_dim;
         lh.scalar = 1.0f / (float)cfg_.global_batch; lh.mu = 0; lh.n = mb;
         lh.e = cfg_.split ? dz_lo_all_[L_] : nullptr;
+        lh.f = loss_zero_copy_ ? loss_target() : nullptr;
         ops_.push_back(lh);
     }
     const bool fuse = (cfg_.dp_mode == 0);
@@ -837,9 +847,11 @@ void PipeEngine::build_coalesced() {
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
     }
-    Op cp;
-    cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
-    ops_.push_back(cp);
+    if (!loss_zero_copy_) {
+        Op cp;
+        cp.kind = OP_MEMCPY_LOSS; cp.stream = 0; cp.a = loss_host_ + cur_set_ * std::max(cfg_.n_mu, 16);
+        ops_.push_back(cp);
+    }
 }
 
 void PipeEngine::finish_build() {
@@ -889,7 +901,7 @@ void PipeEngine::exec(const Op& op) {
         case OP_RECORD: CUDA_CHECK(cudaEventRecord(events_[op.event], st)); break;
         case OP_GEMM: CUDA_CHECK(gemm_launch(gemms_[op.gemm], st)); break;
         case OP_LOSS_HEAD:
-            CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, loss_dev_ + op.mu, op.rows,
+            CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, (op.f ? op.f : loss_dev_) + op.mu, op.rows,
                                         op.cols, op.scalar, st, (int)op.n, op.e));
             break;
         case OP_SOFTMAX:

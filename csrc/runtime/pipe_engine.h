@@ -63,6 +63,7 @@ struct Op {
     std::vector<CommItem> comm;
     // generic pointers for the small kernels
     float *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr, *e = nullptr;   // e: lo twin of the output (split mode)
+    float* f = nullptr;        // loss head: where the loss values go when not the default device scratch
     int lda = 0, ldb = 0, ldc = 0, ldd = 0, rows = 0, cols = 0;
     float scalar = 0.f;
     int64_t n = 0;
@@ -140,6 +141,7 @@ private:
     void select_set(int set);
     void finish_build();
     int new_event();
+    float* loss_target() const;
     void maybe_splitk(GemmPlan& g);
     void emit_wait(int stream, int ev);
     int emit_record(int stream);
@@ -174,6 +176,7 @@ private:
     std::vector<cudaEvent_t> timing_events_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exposed_pairs_, busy_pairs_;
     bool comm_timing_ = false;
+    bool loss_zero_copy_ = false;
     std::vector<GemmPlan> gemms_;
     std::vector<FusedDpPlan> dp_plans_;
     std::vector<ChainPlan> chain_plans_;

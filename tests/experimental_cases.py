@@ -145,3 +145,28 @@ def test_chain_multicast_cluster_is_bitwise_identical(monkeypatch, precision, n_
     assert got == ref                                      # same MMAs in the same order: identical losses
     assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
 
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: loss values stored straight into pinned host memory (SSB_LOSS_ZEROCOPY=1), no D2H copy node.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env", [{}, {"SSB_NO_CHAIN": "1"}, {"SSB_NO_COALESCE": "1"}])
+def test_loss_zero_copy_readback_matches(monkeypatch, env):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_LOSS_ZEROCOPY", "1")
+    tr = Trainer(SIZES, lr=0.1)
+    assert "loss_d2h" not in tr.engine.plan_text(0)
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref
+    # pipelined read-back: loss of step i is returned by call i + 1
+    tr2 = Trainer(SIZES, lr=0.1)
+    lag = [tr2.step_pipelined(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)] + [tr2.flush()]
+    assert lag[0] is None and lag[1:] == ref
