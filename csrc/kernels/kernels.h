@@ -89,6 +89,19 @@ int gemm_splitk_choice(const GemmPlan& plan, int num_sms);
 size_t gemm_splitk_workspace_floats(const GemmPlan& plan, int k_splits);
 const char* gemm_plan_enable_splitk(GemmPlan* plan, int k_splits, float* workspace, unsigned int* counters);
 cudaError_t gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+// Grouped launch of several WGRAD plans (different layers) as ONE grid: a device table holds one entry per CTA.
+struct alignas(128) GemmGroupEntry {
+    CUtensorMap tmA, tmB, tmC, tmAlo, tmBlo;
+    GemmParams p;
+    int bx, by;                    // tile coordinates of this CTA inside its GEMM
+};
+struct GemmGroupPlan {
+    GemmGroupEntry* entries_dev;
+    int n, smem_bytes, wlo, n_gemms;
+};
+const char* gemm_group_plan(GemmGroupPlan* out, const GemmPlan* plans, int n_plans);
+cudaError_t gemm_group_launch(const GemmGroupPlan& plan, cudaStream_t stream);
+void gemm_group_free(GemmGroupPlan* plan);
 cudaError_t gemm_configure();   // opt every instantiation into > 48 KB dynamic smem (call outside graph capture)
 int gemm_kernel_count();   // number of launches issued so far by this module (bench accounting)
 

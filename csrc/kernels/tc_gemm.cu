@@ -20,7 +20,9 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace ssb {
 
@@ -37,11 +39,12 @@ static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-
 // WLO (WGRAD with the SGD update fused, fp32-equivalent mode): after the -lr*dW tile has been reduce-added into
 // W, the same CTA reads the updated tile back from L2 and writes its lo twin (W - trunc_tf32(W)), which removes
 // the arena-wide split kernel (and its graph edge) from the end of every step.
-template <int MODE, bool SPLITK = false, bool WLO = false>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+// The body is shared by the one-GEMM-per-launch kernels below and by the grouped weight-gradient kernel (several
+// layers' tiles in ONE launch, tensor maps and parameters read from a device table).
+template <int MODE, bool SPLITK, bool WLO>
+__device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                             const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, const GemmParams& p, const int bx,
+                                             const int by, const int bz) {
     constexpr bool A_MN = (MODE != GEMM_FWD);
     constexpr bool B_MN = (MODE == GEMM_WGRAD);
 
@@ -51,13 +54,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem_gen = smem_raw + (smem_base - raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBlockM;
-    const int n0 = blockIdx.y * p.block_n;
+    const int m0 = bx * kBlockM;
+    const int n0 = by * p.block_n;
     int num_kb = (p.k_total + kBlockK - 1) / kBlockK;
     int kb0 = 0;                                           // first k-block of this CTA
     if constexpr (SPLITK) {
         const int per = (num_kb + p.k_splits - 1) / p.k_splits;   // host guarantees every split is non-empty
-        kb0 = (int)blockIdx.z * per;
+        kb0 = bz * per;
         num_kb = min(per, num_kb - kb0);
     }
     const uint32_t b_bytes = p.block_n * 128u;
@@ -77,7 +80,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
 
-    const bool db_active = (MODE == GEMM_WGRAD) && (p.db != nullptr) && (blockIdx.y == 0);
+    const bool db_active = (MODE == GEMM_WGRAD) && (p.db != nullptr) && (by == 0);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -217,9 +220,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
         if constexpr (SPLITK) {
             // ---- split-K: publish the raw partial, last arriver reduces (fixed split order) + epilogue
-            const int tile = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+            const int tile = (int)(by * gridDim.x + bx);
             const size_t tile_floats = (size_t)p.block_n * kBlockM;
-            float* ws = p.partial + ((size_t)tile * p.k_splits + blockIdx.z) * tile_floats;
+            float* ws = p.partial + ((size_t)tile * p.k_splits + bz) * tile_floats;
             for (int c = 0; c < p.block_n; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + c, v);
@@ -395,6 +398,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+template <int MODE, bool SPLITK = false, bool WLO = false>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+    tc_gemm_body<MODE, SPLITK, WLO>(tmA, tmB, tmC, tmAlo, tmBlo, p, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+}
+
+// ---- grouped weight-gradient launch: the tiles of SEVERAL layers' WGRAD GEMMs in one grid (one table entry per CTA).
+// Removes the fork / join of one graph node per layer from the end of a step; combined with WLO (no split kernel)
+// and the zero-copy loss the whole training step is two graph nodes: chain kernel -> grouped wgrad.
+template <bool WLO>
+__global__ void __launch_bounds__(kThreads, 1) tc_wgrad_group_kernel(const GemmGroupEntry* __restrict__ entries) {
+    const GemmGroupEntry& e = entries[blockIdx.x];
+    const GemmParams p = e.p;                      // private copy: the body reads these fields in every loop
+    tc_gemm_body<GEMM_WGRAD, false, WLO>(e.tmA, e.tmB, e.tmC, e.tmAlo, e.tmBlo, p, e.bx, e.by, 0);
+}
+
 // =========================================================================== host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -568,6 +589,42 @@ const char* gemm_plan_enable_splitk(GemmPlan* plan, int k_splits, float* workspa
     return nullptr;
 }
 
+const char* gemm_group_plan(GemmGroupPlan* out, const GemmPlan* plans, int n_plans) {
+    *out = GemmGroupPlan{};
+    if (n_plans < 1) return "gemm_group_plan: no plans";
+    std::vector<GemmGroupEntry> host;
+    int smem = 0;
+    const bool wlo = plans[0].p.W_lo != nullptr && plans[0].p.fuse_sgd;
+    for (int i = 0; i < n_plans; ++i) {
+        const GemmPlan& g = plans[i];
+        if (g.mode != GEMM_WGRAD) return "gemm_group_plan: only weight-gradient GEMMs can be grouped";
+        if (g.p.k_splits > 1) return "gemm_group_plan: split-K plans cannot be grouped";
+        if ((g.p.W_lo != nullptr && g.p.fuse_sgd) != wlo) return "gemm_group_plan: mixed lo-twin modes";
+        if (g.smem_bytes > smem) smem = g.smem_bytes;
+        for (unsigned by = 0; by < g.grid.y; ++by)
+            for (unsigned bx = 0; bx < g.grid.x; ++bx) {
+                GemmGroupEntry e;
+                memset(&e, 0, sizeof(e));
+                e.tmA = g.tmA; e.tmB = g.tmB; e.tmC = g.tmC; e.tmAlo = g.tmAlo; e.tmBlo = g.tmBlo;
+                e.p = g.p; e.bx = (int)bx; e.by = (int)by;
+                host.push_back(e);
+            }
+    }
+    GemmGroupEntry* dev = nullptr;
+    if (cudaMalloc(&dev, host.size() * sizeof(GemmGroupEntry)) != cudaSuccess) return "gemm_group_plan: cudaMalloc failed";
+    if (cudaMemcpy(dev, host.data(), host.size() * sizeof(GemmGroupEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dev);
+        return "gemm_group_plan: table upload failed";
+    }
+    out->entries_dev = dev; out->n = (int)host.size(); out->smem_bytes = smem; out->wlo = wlo ? 1 : 0; out->n_gemms = n_plans;
+    return nullptr;
+}
+
+void gemm_group_free(GemmGroupPlan* plan) {
+    if (plan->entries_dev) cudaFree(plan->entries_dev);
+    plan->entries_dev = nullptr;
+}
+
 static std::atomic<int> g_launches{0};
 int gemm_kernel_count() { return g_launches.load(); }
 
@@ -581,10 +638,23 @@ cudaError_t gemm_configure() {
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_wgrad_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_wgrad_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     g_configured = true;
     return cudaSuccess;
+}
+
+cudaError_t gemm_group_launch(const GemmGroupPlan& plan, cudaStream_t stream) {
+    if (!g_configured) {
+        cudaError_t e = gemm_configure();
+        if (e != cudaSuccess) return e;
+    }
+    if (plan.wlo) tc_wgrad_group_kernel<true><<<plan.n, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev);
+    else tc_wgrad_group_kernel<false><<<plan.n, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev);
+    g_launches.fetch_add(plan.n_gemms, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 template <int MODE>

@@ -67,6 +67,7 @@ PipeEngine::~PipeEngine() {
     for (auto e : timing_events_) cudaEventDestroy(e);
     for (auto s : streams_) cudaStreamDestroy(s);
     for (auto& cp : chain_plans_) chain_plan_free(&cp);
+    for (auto& gp : group_plans_) gemm_group_free(&gp);
     for (auto p : owned_) cudaFree(p);
     if (loss_host_) cudaFreeHost(loss_host_);
 }
@@ -760,6 +761,10 @@ void PipeEngine::build_coalesced() {
     // opt-in (SSB_FUSE_WLO=1, awaiting hardware validation): the SGD-fused wgrad kernels also refresh the lo twin
     // of the weights, so the arena-wide split kernel at the end of the step disappears
     const bool fuse_wlo = fuse && cfg_.split && getenv("SSB_FUSE_WLO") != nullptr && atoi(getenv("SSB_FUSE_WLO")) > 0;
+    // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
+    // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
+    const bool group_wgrad = fuse && chain && getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
+    std::vector<GemmPlan> grouped;
     int ev_bump = -1;
     if (fused_dp) {
         if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
@@ -809,14 +814,17 @@ void PipeEngine::build_coalesced() {
             ops_.push_back(fo);
             continue;
         }
-        const int w = sw(l);
-        use(w);
-        emit_wait(w, ev_dz);
-        if (fuse && ev_dg >= 0) emit_wait(w, ev_dg);      // W_l is updated in place: its last reader must be done
+        const int w = group_wgrad ? 0 : sw(l);
+        if (!group_wgrad) {
+            use(w);
+            emit_wait(w, ev_dz);
+            if (fuse && ev_dg >= 0) emit_wait(w, ev_dg);  // W_l is updated in place: its last reader must be done
+        }
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
         if (fuse_wlo) g.p.W_lo = W_lo_ + ls.offset;       // the epilogue refreshes the lo twin of its own tile
+        if (group_wgrad) { grouped.push_back(g); continue; }   // launched together after the loop
         add_gemm(g, w, l);
         if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
             const int ev_g = emit_record(w);
@@ -826,6 +834,14 @@ void PipeEngine::build_coalesced() {
             ar.kind = OP_ALLREDUCE; ar.stream = s_dp_; ar.a = Gl(l); ar.n = (int64_t)ls.out * ls.ld; ar.layer = l;
             ops_.push_back(ar);
         }
+    }
+    if (group_wgrad && !grouped.empty()) {
+        GemmGroupPlan gp;
+        check(gemm_group_plan(&gp, grouped.data(), (int)grouped.size()));
+        group_plans_.push_back(gp);
+        Op go;
+        go.kind = OP_WGRAD_GROUP; go.stream = 0; go.gemm = (int)group_plans_.size() - 1;
+        ops_.push_back(go);
     }
     if (!fuse && !fused_dp) {
         const int ev_main = emit_record(0);
@@ -860,7 +876,8 @@ void PipeEngine::finish_build() {
         if (op.kind == OP_GEMM || op.kind == OP_LOSS_HEAD || op.kind == OP_SOFTMAX || op.kind == OP_RELU_MASK ||
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
             op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD ||
-            op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT || op.kind == OP_PP_CREDIT || op.kind == OP_PP_BUMP)
+            op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT || op.kind == OP_PP_CREDIT || op.kind == OP_PP_BUMP ||
+            op.kind == OP_WGRAD_GROUP)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -900,6 +917,7 @@ void PipeEngine::exec(const Op& op) {
         case OP_WAIT: CUDA_CHECK(cudaStreamWaitEvent(st, events_[op.event], 0)); break;
         case OP_RECORD: CUDA_CHECK(cudaEventRecord(events_[op.event], st)); break;
         case OP_GEMM: CUDA_CHECK(gemm_launch(gemms_[op.gemm], st)); break;
+        case OP_WGRAD_GROUP: CUDA_CHECK(gemm_group_launch(group_plans_[op.gemm], st)); break;
         case OP_LOSS_HEAD:
             CUDA_CHECK(launch_loss_head(op.a, op.lda, op.b, op.ldb, op.c, op.ldc, op.d, op.ldd, (op.f ? op.f : loss_dev_) + op.mu, op.rows,
                                         op.cols, op.scalar, st, (int)op.n, op.e));
@@ -961,6 +979,7 @@ void PipeEngine::exec(const Op& op) {
 static const char* op_name(int kind) {
     switch (kind) {
         case OP_GEMM: return "gemm";
+        case OP_WGRAD_GROUP: return "wgrad_group";
         case OP_LOSS_HEAD: return "loss_head";
         case OP_SOFTMAX: return "softmax";
         case OP_RELU_MASK: return "relu_mask";

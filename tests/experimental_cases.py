@@ -170,3 +170,43 @@ def test_loss_zero_copy_readback_matches(monkeypatch, env):
     tr2 = Trainer(SIZES, lr=0.1)
     lag = [tr2.step_pipelined(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)] + [tr2.flush()]
     assert lag[0] is None and lag[1:] == ref
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Experimental: all layers' weight-gradient tiles in ONE launch (SSB_WGRAD_GROUP=1); with the lo-twin-refreshing
+# epilogue and the zero-copy loss the whole step is two graph nodes.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_wgrad_group_launch_is_bitwise_identical(monkeypatch, precision):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1, precision=precision)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_WGRAD_GROUP", "1")
+    tr = Trainer(SIZES, lr=0.1, precision=precision)
+    plan = tr.engine.plan_text(0)
+    assert "wgrad_group" in plan and " gemm " not in plan
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
+
+
+def test_two_node_step_all_optins_together(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+    from shallowspeed_b200.parallel.plan_check import check_plan
+
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    base = Trainer(SIZES, lr=0.1)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    for k in ("SSB_WGRAD_GROUP", "SSB_FUSE_WLO", "SSB_LOSS_ZEROCOPY", "SSB_CHAIN_MC"):
+        monkeypatch.setenv(k, "1")
+    tr = Trainer(SIZES, lr=0.1)
+    stats = check_plan(tr.engine.plan_text(0))
+    assert stats["kernels_and_copies"] == 2, tr.engine.plan_text(0)      # chain kernel + grouped wgrad, nothing else
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref and torch.equal(tr.model.arena.weights, base.model.arena.weights)
