@@ -763,7 +763,8 @@ void PipeEngine::build_coalesced() {
     const bool fuse_wlo = fuse && cfg_.split && getenv("SSB_FUSE_WLO") != nullptr && atoi(getenv("SSB_FUSE_WLO")) > 0;
     // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
     // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
-    const bool group_wgrad = fuse && chain && getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
+    // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
+    const bool group_wgrad = (fuse || cfg_.dp_mode == 3) && chain && getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
     std::vector<GemmPlan> grouped;
     int ev_bump = -1;
     if (fused_dp) {
