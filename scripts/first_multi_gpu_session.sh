@@ -27,6 +27,9 @@ for comm in fused nccl nvls; do
     timeout 300 python bench.py --gpus "$N" --comm "$comm" --steps 300 --warmup 50 2>/dev/null | tail -1 | tee -a "$OUT/bench_dp_transports.jsonl"
 done
 
+echo "-- nvls + grouped wgrad + the single-GPU opt-ins that passed (edit the list after first_gpu_session.sh)"
+SSB_WGRAD_GROUP=1 timeout 300 python bench.py --gpus "$N" --comm nvls --steps 300 --warmup 50 2>/dev/null | tail -1 | tee -a "$OUT/bench_dp_transports.jsonl"
+
 echo "== 4. wide model (two-shot regime): hidden 4096 x 4"
 for comm in fused nccl nvls; do
     timeout 300 python bench.py --gpus "$N" --comm "$comm" --hidden 4096 --n-layers 4 --seed-mode index --precision tf32 \
