@@ -444,3 +444,140 @@ def max_in_flight(schedule) -> int:
         elif isinstance(ins, (BackwardGradAcc, BackwardGradAllReduce)):
             cur -= 1
     return peak
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Stream-level model of the PEER-MEMORY pipeline transport (csrc/runtime/pipe_engine.cpp, pp_ctx_ branch of
+# plan_per_mubatch): the native executor lowers a stage's instruction stream to ops on CUDA streams; with the one-sided
+# transport a comm group becomes, on ONE comm stream, [wait for the producing compute event, push] per send followed by
+# one flag wait per receive.  Pushes additionally wait for the consumer's credit of the previous step.  This simulation
+# replays that lowering for all stages over several steps and reports a deadlock if the stream programs can block each
+# other (e.g. a flag wait queued in front of a push the neighbour is waiting for).
+# ------------------------------------------------------------------------------------------------------------
+def simulate_one_sided(schedules: Sequence, n_steps: int = 3, n_mu_streams: int = 4, sends_first: bool = True) -> dict:
+    """``sends_first=False`` models the WRONG lowering (flag waits queued in front of the pushes of the same group) and
+    exists so the tests can show that this model does detect the resulting cross-stage deadlock."""
+    S = len(schedules)
+    progs = []          # per stage: {stream name: [op, ...]}, op = (kind, payload)
+    for s, sc in enumerate(schedules):
+        stream = flatten(list(sc.steps()))
+        streams = {"comm": []}
+        ev_in, ev_gout, ev_fwd, ev_bwd = {}, {}, {}, {}
+        n_ev = 0
+        for it in _itemize(stream):
+            if it.kind == "group":
+                recvs = []
+                sends = [i for i in it.instrs if isinstance(i, (SendActivations, SendInputGrad))]
+                rest = [i for i in it.instrs if not isinstance(i, (SendActivations, SendInputGrad))]
+                mu_of = _resolve_group_mubatches(stream, it)
+                def emit_waits():
+                    for ins in rest:
+                        mu = mu_of[id(ins)]
+                        is_act = isinstance(ins, RecvActivations)
+                        streams["comm"].append(("wait_flag", ("act" if is_act else "dz", s, mu)))
+                        recvs.append((mu, is_act))
+
+                if not sends_first:
+                    emit_waits()
+                for ins in sends:
+                    mu = mu_of[id(ins)]
+                    is_act = isinstance(ins, SendActivations)
+                    dep = (ev_fwd if is_act else ev_bwd).get(mu)
+                    if dep is not None:
+                        streams["comm"].append(("wait_event", dep))
+                    streams["comm"].append(("push", ("act" if is_act else "dz", s + 1 if is_act else s - 1, mu)))
+                if sends_first:
+                    emit_waits()
+                if recvs:
+                    ev = (s, n_ev); n_ev += 1
+                    streams["comm"].append(("record", ev))
+                    for mu, is_act in recvs:
+                        (ev_in if is_act else ev_gout)[mu] = ev
+                continue
+            ins = it.instrs[0]
+            if isinstance(ins, (Forward, BackwardGradAcc, BackwardGradAllReduce)):
+                mu = ins.mubatch_id
+                name = f"c{mu % n_mu_streams}"
+                ops = streams.setdefault(name, [])
+                is_f = isinstance(ins, Forward)
+                dep = (ev_in if is_f else ev_gout).pop(mu, None)
+                if dep is not None:
+                    ops.append(("wait_event", dep))
+                ops.append(("compute", ("F" if is_f else "B", mu)))
+                ev = (s, n_ev); n_ev += 1
+                ops.append(("record", ev))
+                (ev_fwd if is_f else ev_bwd)[mu] = ev
+        progs.append(streams)
+
+    arrived = {}                          # (kind, dst_stage, mu) -> last step whose data landed
+    credit = {}                           # (kind, producer_stage) -> last step whose slots the consumer released
+    finished_steps = [0] * S
+    stats = {"pushes": 0, "waits": 0}
+    for step in range(1, n_steps + 1):
+        pcs = [{name: 0 for name in progs[s]} for s in range(S)]
+        events = set()
+        active = [True] * S               # stages still inside this step
+        while any(active):
+            progressed = False
+            for s in range(S):
+                if not active[s]:
+                    continue
+                for name, ops in progs[s].items():
+                    while pcs[s][name] < len(ops):
+                        kind, arg = ops[pcs[s][name]]
+                        if kind == "wait_event" and (step, arg) not in events:
+                            break
+                        if kind == "wait_flag" and arrived.get(arg, 0) < step:
+                            break
+                        if kind == "push":
+                            k, dst, mu = arg
+                            if not (0 <= dst < S):
+                                raise ScheduleError(f"stage {s} pushes to stage {dst}")
+                            if credit.get((k, s), 0) < step - 1:
+                                break                      # the consumer still owns the slots of the previous step
+                            arrived[(k, dst, mu)] = step
+                            stats["pushes"] += 1
+                        if kind == "wait_flag":
+                            stats["waits"] += 1
+                        if kind == "record":
+                            events.add((step, arg))
+                        pcs[s][name] += 1
+                        progressed = True
+                if all(pcs[s][n] == len(o) for n, o in progs[s].items()):
+                    # step finished on every stream: hand the receive slots back to the producers
+                    active[s] = False
+                    finished_steps[s] = step
+                    if s > 0:
+                        credit[("act", s - 1)] = step
+                    if s + 1 < S:
+                        credit[("dz", s + 1)] = step
+                    progressed = True
+            if not progressed:
+                where = {s: {n: (o[pcs[s][n]] if pcs[s][n] < len(o) else "done") for n, o in progs[s].items()}
+                         for s in range(S) if active[s]}
+                raise ScheduleError(f"deadlock in the one-sided transport model at step {step}: {where}")
+    stats["steps"] = n_steps
+    return stats
+
+
+def _resolve_group_mubatches(stream, item):
+    """micro-batch carried by every comm instruction of ``item`` (same rule as PipeEngine::build: a receive belongs to
+    the next compute instruction on its buffer, a send to the previous one)."""
+    pos = {id(ins): i for i, ins in enumerate(stream)}
+    out = {}
+    for ins in item.instrs:
+        i = pos[id(ins)]
+        if isinstance(ins, (RecvActivations, RecvOutputGrad)):
+            want = Forward if isinstance(ins, RecvActivations) else (BackwardGradAcc, BackwardGradAllReduce)
+            rng = range(i + 1, len(stream))
+        else:
+            want = Forward if isinstance(ins, SendActivations) else (BackwardGradAcc, BackwardGradAllReduce)
+            rng = range(i - 1, -1, -1)
+        for j in rng:
+            c = stream[j]
+            if isinstance(c, want) and c.buffer_id == ins.buffer_id:
+                out[id(ins)] = c.mubatch_id
+                break
+        else:
+            raise ScheduleError(f"cannot resolve the micro-batch of {ins}")
+    return out

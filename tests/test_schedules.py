@@ -199,3 +199,27 @@ def test_render_schedule_svg(tmp_path):
     txt = out.read_text()
     assert txt.startswith("<svg") and "B3*<" in txt  # 1F1B finishes on the last micro-batch
     assert txt.count(">F") == 9  # 8 forward boxes + the legend
+
+
+@pytest.mark.parametrize("cls", [NaiveParallelSchedule, GPipeSchedule, PipeDreamSchedule, InferenceSchedule])
+def test_one_sided_transport_model_is_deadlock_free(cls):
+    """Stream-level replay of the peer-memory pipeline transport (pushes + flag waits on one comm stream per stage,
+    credits across steps) for every schedule, several pipeline shapes and both 1 and 4 compute streams."""
+    from shallowspeed_b200.parallel.validate import simulate_one_sided
+
+    for M in (1, 2, 4, 5, 8):
+        for S in (2, 3, 4, 8):
+            for nms in (1, 4):
+                stats = simulate_one_sided([cls(M, S, s) for s in range(S)], n_steps=3, n_mu_streams=nms)
+                per_step = (S - 1) * M * (1 if cls is InferenceSchedule else 2)
+                assert stats["pushes"] == stats["waits"] == 3 * per_step
+
+
+def test_one_sided_model_detects_the_wrong_op_order():
+    # flag waits queued in FRONT of the pushes of the same group: 1F1B's [SendAct, RecvGrad] / [SendGrad, RecvAct] pairs
+    # then wait for each other across the stage boundary
+    from shallowspeed_b200.parallel.validate import simulate_one_sided
+
+    with pytest.raises(ScheduleError, match="deadlock in the one-sided transport model"):
+        simulate_one_sided([PipeDreamSchedule(4, 2, s) for s in range(2)], sends_first=False)
+    simulate_one_sided([PipeDreamSchedule(4, 2, s) for s in range(2)], sends_first=True)
