@@ -76,16 +76,22 @@ def sass_census():
     funcs = re.split(r"\n\s*Function : ", text)
     census = ["# SASS evidence (cuobjdump -sass of the in-tree extension, sm_100a)", "",
               "| kernel | UTCHMMA (tcgen05.mma) | LDTM (tcgen05.ld) | UTMALDG (TMA load) | UTMASTG/UTMAREDG (TMA store/reduce) | "
-              "UTCBAR (tcgen05.commit) | MEMBAR.*SYS | ST/LD .SYS (peer flags) | HMMA (legacy) |", "|---|---|---|---|---|---|---|---|---|"]
+              "UTCBAR (tcgen05.commit) | MEMBAR.*SYS | ST/LD .SYS (peer flags) | HMMA (legacy) | .MULTICAST (cluster TMA / commit) | LDGMC (multimem.ld_reduce) |",
+              "|---|---|---|---|---|---|---|---|---|---|---|"]
     for f in funcs[1:]:
         name = f.split("\n", 1)[0].strip()
         if "ssb" not in name:
             continue
         c = lambda pat: len(re.findall(pat, f))
         census.append(f"| `{name[:70]}` | {c(r'UTCHMMA')} | {c(r'LDTM')} | {c(r'UTMALDG')} | {c(r'UTMASTG') + c(r'UTMAREDG')} | "
-                      f"{c(r'UTCBAR')} | {c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'\.SYS') - c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'HMMA') - c(r'UTCHMMA')} |")
+                      f"{c(r'UTCBAR')} | {c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'\.SYS') - c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'HMMA') - c(r'UTCHMMA')} | "
+                      f"{c(r'\.MULTICAST')} | {c(r'LDGMC')} |")
         if "tc_gemm_kernel" in name or "fused_wgrad_dp" in name:
-            short = "fused_wgrad_dp" if "fused_wgrad_dp" in name else "tc_gemm_mode" + re.sub(r".*ILi(\d)E.*", r"\1", name)
+            if "fused_wgrad_dp" in name:
+                short = "fused_wgrad_dp"
+            else:
+                m = re.search(r"ILi(\d)E(?:Lb(\d)ELb(\d)E)?", name)
+                short = "tc_gemm_mode" + m.group(1) + ("_splitk" if m.group(2) == "1" else "") + ("_wlo" if m.group(3) == "1" else "")
             keep = [ln for ln in f.split("\n") if re.search(r"UTC|LDTM|UTMA|SYNCS|MEMBAR|\.SYS|UBLKCP|ELECT|BAR\.", ln)]
             open(os.path.join(OUT, f"sass_{short}.txt"), "w").write(
                 f"// {name}\n// tensor-core / TMA / barrier / system-scope instructions only (full listing: cuobjdump -sass)\n" + "\n".join(keep) + "\n")
