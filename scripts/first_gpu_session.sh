@@ -10,7 +10,7 @@ mkdir -p "$OUT"
 
 echo "== 1. experimental kernels + aux subsystems (xfail markers ignored: real outcome wanted)"
 timeout 300 python -m pytest tests/test_gpu_zz_aux.py -q -k "not experimental" 2>&1 | tail -5 | tee "$OUT/aux_tests.log"
-for group in splitk_forward splitk_dgrad engine_splitk wgrad_fused_sgd_refreshes engine_fused_weight_lo chain_multicast loss_zero_copy wgrad_group_launch two_node_step; do
+for group in splitk weight_lo chain_multicast loss_zero_copy wgrad_group_launch two_node_step; do
     echo "-- experimental group: $group (own process)"
     timeout 300 python -m pytest tests/experimental_cases.py -k "$group" -q -x -p no:cacheprovider 2>&1 | tail -15 | tee -a "$OUT/experimental_tests.log"
 done
