@@ -203,10 +203,15 @@ def test_two_node_step_all_optins_together(monkeypatch):
     xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
     base = Trainer(SIZES, lr=0.1)
     ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
-    for k in ("SSB_WGRAD_GROUP", "SSB_FUSE_WLO", "SSB_LOSS_ZEROCOPY", "SSB_CHAIN_MC"):
+    for k in ("SSB_WGRAD_GROUP", "SSB_FUSE_WLO", "SSB_LOSS_ZEROCOPY"):
         monkeypatch.setenv(k, "1")
     tr = Trainer(SIZES, lr=0.1)
     stats = check_plan(tr.engine.plan_text(0))
     assert stats["kernels_and_copies"] == 2, tr.engine.plan_text(0)      # chain kernel + grouped wgrad, nothing else
     got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
     assert got == ref and torch.equal(tr.model.arena.weights, base.model.arena.weights)
+    # ... and with the multicast chain kernel on top (only meaningful once test_chain_multicast_* passes on its own)
+    monkeypatch.setenv("SSB_CHAIN_MC", "1")
+    tr2 = Trainer(SIZES, lr=0.1)
+    got2 = [tr2.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got2 == ref, "two-node step is fine, the multicast chain kernel on top of it is not"
