@@ -1,6 +1,8 @@
 // Python bindings (torch extension) for the sm_100a kernels and the native runtime.
 #include <torch/extension.h>
 #include <pybind11/stl.h>
+#include <sstream>
+#include <stdexcept>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
@@ -231,6 +233,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         }
         const int per = splits > 0 ? (num_kb + splits - 1) / splits : num_kb;
         return std::make_tuple(splits, per, (int)plan.grid.z, plan.p.stages, plan.smem_bytes, err);
+    });
+    // Exercises the C++ runtime features that break when libstdc++ is linked statically next to torch's dynamic
+    // copy (the round-1 GPU-suite segfault): locale-dependent integer / float formatting and an exception that
+    // crosses a function boundary.  Callable without a GPU (tests/test_native_linkage.py).
+    m.def("selftest_format", [](int v) {
+        std::ostringstream os;
+        os << "v=" << v << " f=" << 1.5 << " h=" << std::hex << 255;
+        try {
+            throw std::runtime_error(os.str());
+        } catch (const std::exception& e) {
+            return std::string(e.what());
+        }
     });
     ssb::bind_runtime(m);
 }
