@@ -34,13 +34,15 @@ def main(argv=None):
     ap.add_argument("--n-mubatches", type=int, default=4)
     ap.add_argument("--data-dir", default="/tmp/ssb_ref_data/mnist_784")
     ap.add_argument("--keep-fp64", action="store_true", help="do not cast the weights back to fp32")
-    ap.add_argument("--threads", type=int, default=0, help="BLAS threads per rank (0 = cores / ranks)")
+    ap.add_argument("--threads", type=int, default=0,
+                    help="BLAS threads per rank; 0 = calibrate: time a few steps at 1,2,4,...,cores/ranks threads and keep the fastest")
     args = ap.parse_args(argv)
 
     world = args.dp * args.pp
-    threads = args.threads or max(1, (os.cpu_count() or 1) // world)
+    max_threads = max(1, (os.cpu_count() or 1) // world)
+    threads = min(args.threads, max_threads) if args.threads else max_threads
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[v] = str(threads)
+        os.environ[v] = str(threads)          # upper bound of the BLAS pool; the sweep below lowers it at run time
     sys.path.insert(0, str(HERE / "mpi_shim"))
     sys.path.insert(0, str(HERE / "_ref"))
     import numpy as np
@@ -77,6 +79,34 @@ def main(argv=None):
 
     for i in range(args.warmup):
         step(i)
+
+    # BLAS thread count: 32x784x128 GEMMs are SLOWER on 128 threads than on a few.  The reference sets nothing, so we
+    # give it its best case: a short calibration over powers of two (every rank takes the same decision: the times are
+    # summed over ranks), then the timed run at the winner.  Outside the reference's code, like the timing itself.
+    sweep = None
+    if not args.threads:
+        try:
+            from threadpoolctl import threadpool_limits
+
+            cands = [t for t in (1, 2, 4, 8, 16, 32, 64, 128, 256) if t <= max_threads] or [1]
+            cal_steps = 8
+            sweep = {}
+            for t in cands * 2:                 # two passes, keep the better one per candidate (shared hosts are noisy)
+                with threadpool_limits(limits=t):
+                    step(0)
+                    MPI.COMM_WORLD.Barrier()
+                    c0 = time.perf_counter()
+                    for i in range(cal_steps):
+                        step(i)
+                    MPI.COMM_WORLD.Barrier()
+                    dt_c = np.array([time.perf_counter() - c0], dtype=np.float64)
+                MPI.COMM_WORLD.Allreduce(MPI.IN_PLACE, dt_c, op=MPI.SUM)
+                ms = round(1e3 * float(dt_c[0]) / world / cal_steps, 4)
+                sweep[t] = min(ms, sweep.get(t, ms))
+            threads = min(sweep, key=sweep.get)
+            limiter = threadpool_limits(limits=threads)   # stays in force for the timed run
+        except ImportError:
+            pass
     MPI.COMM_WORLD.Barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -88,6 +118,7 @@ def main(argv=None):
     if rank == 0:
         dt = max(times)
         return {"ms_per_step": 1e3 * dt / args.steps, "samples_per_s": args.steps * gbs / dt, "threads_per_rank": threads,
+                "thread_sweep": sweep,
                 "weights_dtype": str(model.parameters()[0].data.dtype)}
     return None
 

@@ -355,7 +355,8 @@ class Trainer:
 
     def __init__(self, layer_sizes, global_batch_size=128, n_mubatches=4, lr=0.006, schedule="naive",
                  dp_comm=None, pp_comm=None, grid: Optional[ProcessGrid] = None, comm_mode="fused",
-                 use_graph=True, device=None, seed_mode="shape", precision="fp32", watchdog_s=None, pp_transport=None):
+                 use_graph=True, device=None, seed_mode="shape", precision="fp32", watchdog_s=None, pp_transport=None,
+                 local_batch_size=None):
         from ..models.mlp import MLP
         from ..optimizer import SGD
         from .schedules import SCHEDULE_NAME_TO_CLS
@@ -365,7 +366,10 @@ class Trainer:
         dp, pp = self.dp_comm.Get_size(), self.pp_comm.Get_size()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.global_batch_size, self.n_mubatches = global_batch_size, n_mubatches
-        self.local_batch_size = global_batch_size // dp
+        # local_batch_size: rows this replica processes per step.  Defaults to global / dp; an explicit value lets a
+        # communication-free engine do one replica's share of a bigger job (bench.py's exposed-comm twin): the loss
+        # scale stays 1 / global_batch_size.
+        self.local_batch_size = int(local_batch_size) if local_batch_size else global_batch_size // dp
         self.model = MLP(layer_sizes, self.pp_comm.Get_rank(), pp, global_batch_size, seed_mode=seed_mode).to(self.device)
         self.optimizer = SGD(self.model.parameters(), lr, arena=self.model.arena)
 
