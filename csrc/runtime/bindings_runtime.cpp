@@ -182,18 +182,22 @@ public:
     void stage_inputs(const c10::optional<torch::Tensor>& x, const c10::optional<torch::Tensor>& y) {
         const auto& cfg = engine_->config();
         const int64_t rows = (int64_t)cfg.n_mu * cfg.mb_rows;
-        bool from_host = false;
         const float *xp = nullptr, *yp = nullptr;
         if (x.has_value()) {
             TORCH_CHECK(x->is_contiguous() && x->scalar_type() == torch::kFloat32 && x->numel() == rows * cfg.in_dim, "x shape");
-            xp = x->data_ptr<float>(); from_host = !x->is_cuda();
+            xp = x->data_ptr<float>();
         }
         if (y.has_value()) {
             TORCH_CHECK(y->is_contiguous() && y->scalar_type() == torch::kFloat32 && y->numel() == rows * cfg.out_dim, "y shape");
-            yp = y->data_ptr<float>(); from_host = !y->is_cuda();
+            yp = y->data_ptr<float>();
         }
-        engine_->stage_inputs(xp, yp, from_host);
+        engine_->stage_inputs(xp, yp);
+        // the copies are asynchronous: keep the source tensors alive until a later staging call of the same set
+        // (which first waits for this set's compute, hence for these copies) replaces them
+        held_[hold_i_ & 1] = {x, y};
+        ++hold_i_;
     }
+    int n_mubatches() { return engine_->config().n_mu; }
     void run() { engine_->run(); }
     void synchronize() { engine_->synchronize(); }
     bool wait(double timeout_s) {
@@ -232,6 +236,8 @@ public:
 
 private:
     torch::Tensor weights_, grads_;
+    std::pair<c10::optional<torch::Tensor>, c10::optional<torch::Tensor>> held_[2];
+    unsigned hold_i_ = 0;
     std::shared_ptr<NcclComm> pp_, dp_;
     std::shared_ptr<PyDpContext> dpctx_;
     std::shared_ptr<PyNvlsContext> nvls_;
@@ -281,6 +287,7 @@ void bind_runtime(py::module_& m) {
         .def("boundary_lds", &PyEngine::boundary_lds)
         .def("build", &PyEngine::build)
         .def("stage_inputs", &PyEngine::stage_inputs)
+        .def("n_mubatches", &PyEngine::n_mubatches)
         .def("run", &PyEngine::run)
         .def("synchronize", &PyEngine::synchronize)
         .def("wait", &PyEngine::wait)

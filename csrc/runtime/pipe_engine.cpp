@@ -1072,10 +1072,12 @@ std::pair<double, double> PipeEngine::comm_timing() {
 // Inputs of step i go into staging set i % 2 on the COPY stream; the compute graph of that set waits
 // for the copy, and the next copy into the same set waits until that graph finished reading it.  The
 // host enqueues step i + 1's copy while step i still computes, so H2D traffic hides behind compute.
-void PipeEngine::stage_inputs(const float* x, const float* y, bool from_host) {
+void PipeEngine::stage_inputs(const float* x, const float* y) {
     const int set = fill_set_;
     const size_t rows = (size_t)cfg_.n_mu * cfg_.mb_rows;
-    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    // cudaMemcpyDefault: the driver derives the direction per pointer (UVA), so x and y may live on different sides
+    // (device-resident inputs with pinned-host targets, or the reverse)
+    const cudaMemcpyKind kind = cudaMemcpyDefault;
     CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, ev_done_[set], 0));
     if (x != nullptr && cfg_.is_first)
         CUDA_CHECK(cudaMemcpy2DAsync(x_stage_sets_[set], (size_t)act_ld_[0] * 4, x, (size_t)cfg_.in_dim * 4, (size_t)cfg_.in_dim * 4,

@@ -103,7 +103,7 @@ public:
 
     // input staging ------------------------------------------------------------------
     // dense row-major host/device sources: x [n_mu*mb_rows, in_dim], y [n_mu*mb_rows, out_dim]
-    void stage_inputs(const float* x, const float* y, bool from_host);
+    void stage_inputs(const float* x, const float* y);
     void run();                       // one step (graph launch or eager plan walk) on the main stream
     void synchronize();
     bool wait(double timeout_s);      // watchdog: false if the step in flight did not finish in time

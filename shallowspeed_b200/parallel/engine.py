@@ -223,6 +223,11 @@ class NativeWorker:
         self.lr = optimizer.lr if optimizer is not None else 0.0
         self._dp_ctx = None
         self._nvls_ctx = None
+        # Engines that share a communicator (train + validation worker on one pipeline group) run on their own
+        # non-blocking streams.  NCCL matches p2p operations in issue order per peer and forbids concurrent use of one
+        # communicator, so successive engines are ordered explicitly: ``_order["last"]`` is the engine whose work was
+        # enqueued last on the shared communicators (see ``_enter``).
+        self._order = share._order if share is not None else {"last": None}
         if share is not None:
             self._pp_nccl, self._dp_nccl = share._pp_nccl, share._dp_nccl
         else:
@@ -282,9 +287,22 @@ class NativeWorker:
         return eng
 
     # ------------------------------------------------------------------ Worker surface
+    def _enter(self, eng):
+        """Order ``eng`` behind whichever engine used the shared communicators last (train <-> validation switches).
+        An engine's main stream joins all of its side streams at the end of a run, and its next run forks from the main
+        stream, so one event edge main(prev) -> main(eng) serialises every NCCL operation of the two engines, on every
+        stage, without a host synchronisation."""
+        prev = self._order["last"]
+        if prev is not None and prev is not eng:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.ExternalStream(prev.main_stream(), device=self.device))
+            torch.cuda.ExternalStream(eng.main_stream(), device=self.device).wait_event(ev)
+        self._order["last"] = eng
+
     def execute(self, sched: Schedule, batch_id: int):
         eng = self.engine_for(sched)
         x, y = self.dataset.load_batch(batch_id)
+        self._enter(eng)
         eng.stage_inputs(x if sched.is_first_stage else None, y if sched.is_last_stage else None)
         eng.run()
         self._last_engine = eng
@@ -292,6 +310,7 @@ class NativeWorker:
     def step_from(self, sched: Schedule, x, y):
         """Run one step on explicit (pinned-host or device) batch tensors."""
         eng = self.engine_for(sched)
+        self._enter(eng)
         eng.stage_inputs(x if sched.is_first_stage else None, y if sched.is_last_stage else None)
         eng.run()
         self._last_engine = eng
@@ -303,8 +322,7 @@ class NativeWorker:
         ``worker.output_buffers[0]``)."""
         eng = self._last_engine
         eng.synchronize()
-        n_mu = 1
-        return [eng.probs(mu) for mu in range(n_mu)]
+        return [eng.probs(mu) for mu in range(int(eng.n_mubatches()))]
 
     def batch_loss(self):
         if self._last_engine is None or self.stage_id != self.pipeline_depth - 1:

@@ -175,3 +175,101 @@ PP_PEER_EXPERIMENTAL = pytest.mark.xfail(strict=False, reason="peer-memory pipel
 @pytest.mark.parametrize("dp,pp,sched", [(1, 2, "naive"), (1, 2, "gpipe"), (1, 2, "pipedream"), (1, 4, "gpipe"), (2, 2, "pipedream")])
 def test_pp_peer_transport_matches_oracle(dp, pp, sched, tmp_path):
     _run(dp, pp, sched, "fused", tmp_path, extra_env={"SSB_PP_PEER": "1"})
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Train <-> validation alternation on ONE pipeline communicator (advisor finding, round 1): the validation worker's
+# engine and the training worker's engine share the native ncclComm but own separate streams and graphs; without an
+# explicit edge between them stage 0 could enqueue training sends while its validation sends were still pending.
+# ---------------------------------------------------------------------------------------------------------
+ROUNDS, VAL_BATCHES, TRAIN_STEPS = 3, 3, 3
+
+
+def _alternation_worker(rank, world, pp, sched_name, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    from shallowspeed_b200.dataset import Dataset, synthetic_mnist
+    from shallowspeed_b200.layers import MLP
+    from shallowspeed_b200.optimizer import SGD
+    from shallowspeed_b200.parallel.comm import ProcessGrid, make_torch_comms
+    from shallowspeed_b200.parallel.engine import NativeWorker
+    from shallowspeed_b200.pipe import SCHEDULE_NAME_TO_CLS, InferenceSchedule
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    grid = ProcessGrid(1, pp, rank)
+    dp_comm, pp_comm = make_torch_comms(grid)
+    model = MLP(SIZES, grid.stage, pp, GBS).to(f"cuda:{rank}")
+    opt = SGD(model.parameters(), LR, arena=model.arena)
+    x, y = synthetic_mnist(n=GBS * ROUNDS * TRAIN_STEPS)
+    ds = Dataset(None, GBS, GBS // N_MU, device=f"cuda:{rank}")
+    ds.local_batch_size = GBS
+    ds.from_arrays(x, y)
+    vds = Dataset(None, GBS, GBS, device=f"cuda:{rank}")
+    vds.local_batch_size = GBS
+    vds.from_arrays(x[: GBS * VAL_BATCHES], y[: GBS * VAL_BATCHES])
+    w = NativeWorker(dp_comm, pp_comm, model, ds, opt, grid=grid)
+    vw = NativeWorker(None, pp_comm, model, vds, None, grid=grid, comm_mode="nccl", share=w)
+    sched = SCHEDULE_NAME_TO_CLS[sched_name](N_MU, pp, grid.stage)
+    probs = []
+    step = 0
+    for _r in range(ROUNDS):
+        # NO host synchronisation between the two phases on the non-last stages: exactly the situation train.py creates
+        for b in range(VAL_BATCHES):
+            vw.execute(InferenceSchedule(1, pp, grid.stage), b)
+            if grid.stage == pp - 1:
+                probs.append(vw.output_buffers[0].cpu().clone())
+        for _s in range(TRAIN_STEPS):
+            w.execute(sched, step)
+            step += 1
+    w.sync_to_model()
+    torch.save({"params": [p.data.cpu().clone() for p in model.parameters()], "probs": probs}, os.path.join(out_dir, f"stage{grid.stage}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pp,sched", [(2, "gpipe"), (2, "pipedream")])
+def test_train_eval_alternation_on_one_pipeline_comm(pp, sched, tmp_path):
+    import torch.multiprocessing as mp
+
+    from shallowspeed_b200.dataset import Dataset, synthetic_mnist
+    from shallowspeed_b200.layers import MLP
+    from shallowspeed_b200.optimizer import SGD
+    from shallowspeed_b200.pipe import InferenceSchedule, NaiveParallelSchedule, Worker
+
+    if torch.cuda.device_count() < pp:
+        pytest.skip(f"needs {pp} GPUs")
+    port = 29950 + (os.getpid() + len(sched)) % 40
+    mp.spawn(_alternation_worker, args=(pp, pp, sched, port, str(tmp_path)), nprocs=pp, join=True)
+    got = [torch.load(tmp_path / f"stage{s}.pt") for s in range(pp)]
+    # CPU oracle: the same alternation, sequentially
+    x, y = synthetic_mnist(n=GBS * ROUNDS * TRAIN_STEPS)
+    model = MLP(SIZES, 0, 1, GBS)
+    init = [p.data.clone() for p in model.parameters()]
+    ds = Dataset(None, GBS, GBS // N_MU)
+    ds.local_batch_size = GBS
+    ds.from_arrays(x, y)
+    vds = Dataset(None, GBS, GBS)
+    vds.local_batch_size = GBS
+    vds.from_arrays(x[: GBS * VAL_BATCHES], y[: GBS * VAL_BATCHES])
+    w = Worker(None, None, model, ds, SGD(model.parameters(), LR, arena=model.arena))
+    vw = Worker(None, None, model, vds, None)
+    ref_probs, step = [], 0
+    for _r in range(ROUNDS):
+        model.eval()
+        for b in range(VAL_BATCHES):
+            vw.execute(InferenceSchedule(1, 1, 0), b)
+            ref_probs.append(vw.output_buffers[0].clone())
+        model.train()
+        for _s in range(TRAIN_STEPS):
+            w.execute(NaiveParallelSchedule(N_MU, 1, 0), step)
+            step += 1
+    probs = got[pp - 1]["probs"]
+    assert len(probs) == len(ref_probs)
+    for a, b in zip(probs, ref_probs):
+        assert float((a - b).abs().max()) < 2e-3
+    params = [p for s in range(pp) for p in got[s]["params"]]
+    for p0, a, b in zip(init, params, [p.data for p in model.parameters()]):
+        upd_err = float(((a - p0) - (b - p0)).norm() / ((b - p0).norm() + 1e-12))
+        assert upd_err < 3e-2, upd_err
