@@ -108,8 +108,7 @@ static void linear_dgrad(const Tensor& dz, const Tensor& W, const c10::optional<
 // G[out, in] (+)= dz^T @ x ; db[out] (+)= colsum(dz) ; optionally W -= lr * (G + ...)
 static void linear_wgrad(const Tensor& dz, const Tensor& x, Tensor& G, bool accumulate, const c10::optional<Tensor>& db,
                          int64_t db_stride, const c10::optional<Tensor>& W, double lr, bool fuse_sgd,
-                         const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& x_lo,
-                         const c10::optional<Tensor>& W_lo_out) {
+                         const c10::optional<Tensor>& dz_lo, const c10::optional<Tensor>& x_lo) {
     check_mat(dz, "dz"); check_mat(x, "x"); check_mat(G, "G");
     const int rows = dz.size(0), out = dz.size(1), in = x.size(1);
     TORCH_CHECK(x.size(0) == rows && G.size(0) == out && G.size(1) == in, "linear_wgrad: shape mismatch");
@@ -121,12 +120,6 @@ static void linear_wgrad(const Tensor& dz, const Tensor& x, Tensor& G, bool accu
                                            W.has_value() ? W->data_ptr<float>() : nullptr,
                                            W.has_value() ? ld_of(*W) : 0, (float)lr, fuse_sgd, make_lo(dz_lo, x_lo, c10::nullopt));
     TORCH_CHECK(err == nullptr, "linear_wgrad: ", err ? err : "");
-    if (W_lo_out.has_value()) {     // experimental: refresh the lo twin of the updated weights in the same kernel
-        TORCH_CHECK(fuse_sgd && W.has_value(), "W_lo_out needs fuse_sgd");
-        check_mat(*W_lo_out, "W_lo_out");
-        TORCH_CHECK(W_lo_out->size(0) == out && W_lo_out->size(1) == in && ld_of(*W_lo_out) == ld_of(*W), "W_lo_out geometry");
-        plan.p.W_lo = W_lo_out->data_ptr<float>();
-    }
     cuda_ok(ssb::gemm_launch(plan, cur_stream()), "linear_wgrad launch");
 }
 
@@ -189,7 +182,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("W_lo") = py::none(), py::arg("dz_lo") = py::none(), py::arg("dx_lo") = py::none(), py::arg("k_splits") = 0);
     m.def("linear_wgrad", &linear_wgrad, py::arg("dz"), py::arg("x"), py::arg("G"), py::arg("accumulate"), py::arg("db"),
           py::arg("db_stride"), py::arg("W"), py::arg("lr"), py::arg("fuse_sgd"), py::arg("dz_lo") = py::none(),
-          py::arg("x_lo") = py::none(), py::arg("W_lo_out") = py::none());
+          py::arg("x_lo") = py::none());
     m.def("loss_head", &loss_head);
     m.def("softmax_grad", &softmax_grad);
     m.def("relu_mask_", &relu_mask_);

@@ -52,7 +52,6 @@ struct GemmParams {
     float* partial;
     unsigned int* tile_counter;   // zero before the first launch; re-armed by the kernel
     // WGRAD + fuse_sgd in fp32-equivalent mode (opt-in): also refresh the lo twin of the updated weight tile
-    float* W_lo;                  // same [out, ldw] geometry as W; nullptr = off
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
@@ -97,7 +96,7 @@ struct alignas(128) GemmGroupEntry {
 };
 struct GemmGroupPlan {
     GemmGroupEntry* entries_dev;
-    int n, smem_bytes, wlo, n_gemms;
+    int n, smem_bytes, n_gemms;
 };
 const char* gemm_group_plan(GemmGroupPlan* out, const GemmPlan* plans, int n_plans);
 cudaError_t gemm_group_launch(const GemmGroupPlan& plan, cudaStream_t stream);
@@ -183,18 +182,18 @@ struct ChainParams {
     int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
-    int mc_base;                     // > 0 (multicast variant only): index of the quarter-tile forward weight maps
+    int derive;                      // split mode: lo twins of the streamed tiles are derived on chip (no W_lo / X_lo loads)
     unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only
 };
 struct ChainPlan {
     ChainParams p;
     CUtensorMap* maps_dev;
     int grid, smem_bytes;
-    int cluster;                     // 1, or 4: micro-batch CTAs share the weight stream through TMA multicast
 };
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split = false);
+// split_mode: 0 = single-pass TF32; 1 = 3xTF32 with lo twins LOADED from W_lo / x_lo; 2 = 3xTF32 with lo twins DERIVED on chip
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       const float* W_lo = nullptr, const float* x_lo = nullptr, bool multicast = false);
+                       int split_mode = 0, const float* W_lo = nullptr, const float* x_lo = nullptr);
 bool chain_budget(int mb_rows, bool split, int* kps, int* stages, int* smem_bytes);   // host arithmetic only
 void chain_plan_free(ChainPlan* plan);
 cudaError_t chain_configure();

@@ -24,6 +24,8 @@
 namespace ssb {
 
 static constexpr int kThreads = 320;                      // 2 control warps + 8 epilogue warps
+static constexpr int kSplitWarps = 2;                     // DERIVE: warps 10..11 derive the lo twins of the streamed tiles
+static constexpr int kThreadsDerive = kThreads + 32 * kSplitWarps;
 static constexpr uint32_t kBlockM = 128;
 static constexpr uint32_t kBlockK = 32;
 static constexpr uint32_t kABytes = kBlockM * 128;
@@ -55,35 +57,19 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define DBG(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = gtime(); } while (0)
 
-// ---- cluster helpers (MC variant only)
-__device__ __forceinline__ uint32_t chain_cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void chain_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-}
-// TMA load whose box lands at the same smem offset (and signals the same mbarrier offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
-        : "memory");
-}
-// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-                 : "memory");
-}
-
 // SPLIT (3xTF32) is a compile-time switch: the single-pass TF32 instantiation carries none of the lo-twin code.
-// MC (opt-in, SSB_CHAIN_MC=1): the 4 micro-batch CTAs form a cluster and share the weight stream - CTA r fetches a
-// quarter of every weight tile and multicasts it to all four, so each SM issues 4x fewer L2 requests for the same
-// operand bytes; a ring slot is released only when all four MMA warps have retired their reads of it.
-template <bool SPLIT, bool MC = false>
-__global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
+//
+// DERIVE (SPLIT only, the default fp32 path): the kernel is bound by how fast ONE SM can pull operand bytes out of L2
+// (measured: 55 GB/s per SM through TMA, independent of ring depth and of cluster multicast - profiles/microbench.md),
+// and every micro-batch CTA streams all weights of the stage.  Loading the lo twins W - trunc_tf32(W) doubled those
+// bytes.  In this variant the TMA fetches only the raw fp32 tiles; two extra warps derive the lo twin of every ring
+// slot in shared memory (elementwise, so the swizzled layout carries over unchanged), fence it to the async proxy and
+// hand the slot to the MMA warp through a second per-slot mbarrier.  The derivation runs ahead of the math like the
+// loads do (weights do not depend on activations) and moves 123 GB/s per SM, so the ring stays ingest-bound at HALF
+// the bytes; the W_lo arena, its refresh kernel after every optimizer step and the X_lo loads disappear.
+template <bool SPLIT, bool DERIVE = false>
+__global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_chain_kernel(const ChainParams p) {
+    static_assert(SPLIT || !DERIVE, "DERIVE is a variant of the 3xTF32 kernel");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t smem_base = (raw + 1023u) & ~1023u;
@@ -104,20 +90,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     const uint32_t bar_base = abuf0 + n_abuf * abuf_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+    auto split_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };   // DERIVE: lo twin of slot s is ready
+    const uint32_t tmem_full_bar = bar_base + 8u * (3 * p.stages);
     const uint32_t act_ready_bar = tmem_full_bar + 8u;
     const uint32_t tmem_slot = act_ready_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (3 * p.stages + 2));
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)N) tmem_cols <<= 1;
     // loss-head transpose scratch [N][kScratchLd] floats, behind the barriers (128 B further)
-    const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
+    const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (3 * p.stages + 2) + 128u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), MC ? 4 : 1);             // MC: the slot is rewritten by all four producers
+            mbar_init(empty_bar(s), 1);
+            mbar_init(split_bar(s), kSplitWarps);            // one arrive per splitter warp (DERIVE)
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(act_ready_bar, 8);                         // one arrive per epilogue warp
@@ -131,11 +119,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    uint32_t crank = 0;
-    if constexpr (MC) {
-        crank = chain_cluster_rank();
-        chain_cluster_sync();                                // every peer's barriers exist before anyone multicasts
-    }
 
     // number of backward GEMMs: layers L..lo (layer 1's dgrad is skipped on the first stage)
     const int bwd_lo = p.first_stage ? 2 : 1;
@@ -162,20 +145,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (SPLIT ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * ((SPLIT && !DERIVE) ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
-                                if constexpr (MC) {      // my quarter (32 of the 128 weight rows) of the tile, to all four CTAs
-                                    tma_load_2d_mc(a_dst + j * kABytes + crank * kPanelBytes, p.maps + p.mc_base + (l - 1), full_bar(s),
-                                                   (kb0 + j) * kBlockK, (int)crank * 32, (uint16_t)0xF);
-                                } else
                                 tma_load_2d(a_dst + j * kABytes, p.maps + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                 if (with_x)
                                     tma_load_2d(a_dst + stage_b_off + j * b_bytes, p.maps + 2 * L, full_bar(s), (kb0 + j) * kBlockK, row0);
-                                if (SPLIT) {
-                                    if constexpr (MC) {
-                                        tma_load_2d_mc(a_dst + half_stage + j * kABytes + crank * kPanelBytes, p.maps + p.mc_base + L + (l - 1),
-                                                       full_bar(s), (kb0 + j) * kBlockK, (int)crank * 32, (uint16_t)0xF);
-                                    } else
+                                if (SPLIT && !DERIVE) {
                                     tma_load_2d(a_dst + half_stage + j * kABytes, p.maps + lo_base + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                     if (with_x)
                                         tma_load_2d(a_dst + half_stage + stage_b_off + j * b_bytes, p.maps + lo_base + 2 * L, full_bar(s),
@@ -196,24 +171,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (SPLIT ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * ((SPLIT && !DERIVE) ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
-                                if constexpr (MC) {      // panel `crank` of the four [32 k x 32 m] panels, to all four CTAs
-                                    tma_load_2d_mc(a_dst + j * kABytes + crank * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s),
-                                                   32 * (int)crank, (kb0 + j) * kBlockK, (uint16_t)0xF);
-                                    if (SPLIT)
-                                        tma_load_2d_mc(a_dst + half_stage + j * kABytes + crank * kPanelBytes,
-                                                       p.maps + lo_base + 2 * (l - 1) + 1, full_bar(s), 32 * (int)crank, (kb0 + j) * kBlockK,
-                                                       (uint16_t)0xF);
-                                } else {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     tma_load_2d(a_dst + j * kABytes + i * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s), 32 * i,
                                                 (kb0 + j) * kBlockK);
-                                    if (SPLIT)
+                                    if (SPLIT && !DERIVE)
                                         tma_load_2d(a_dst + half_stage + j * kABytes + i * kPanelBytes, p.maps + lo_base + 2 * (l - 1) + 1,
                                                     full_bar(s), 32 * i, (kb0 + j) * kBlockK);
-                                }
                                 }
                             }
                         }
@@ -240,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     const int cnt = min(p.kps, nkb - kb0);
                     const int s = it % p.stages;
                     mbar_wait(full_bar(s), (it / p.stages) & 1);
+                    if constexpr (DERIVE) mbar_wait(split_bar(s), (it / p.stages) & 1);   // lo twin derived + fenced
                     tc_fence_after();
                     if (kb0 + cnt >= nkb && lane == 0) DBG(1, 3 * gemm_i + 1);
                     const uint32_t a_src = smem_base + s * stage_bytes;
@@ -267,8 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
                                           ((kb0 + j) | k4) != 0 ? 1u : 0u);
                         }
-                        if constexpr (MC) umma_commit_mc(empty_bar(s), (uint16_t)0xF);   // frees the slot in all four CTAs
-                        else umma_commit(empty_bar(s));
+                        umma_commit(empty_bar(s));
                         if (kb0 + cnt >= nkb) umma_commit(tmem_full_bar);
                     }
                     __syncwarp();
@@ -294,6 +260,48 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 }
             }
         }
+    } else if (DERIVE && warp >= kThreads / 32) {
+        // ============================================================ lo-twin splitters (DERIVE)
+        // Same slot sequence as the producer.  Per slot: wait for the TMA bytes, lo = x - trunc_tf32(x) for the `cnt`
+        // weight tiles (and the X tiles of layer 1) into the slot's second half at the same offsets, make the generic-
+        // proxy writes visible to the async proxy (tcgen05.mma reads operands through it), arrive on split_bar.
+        // The slot cannot be rewritten under us: the producer re-arms it only after the MMAs that read it retired.
+        const int st = (int)threadIdx.x - kThreads;              // 0 .. 127
+        constexpr int kSplitThreads = 32 * kSplitWarps;
+        int it = 0;
+        auto derive = [&](int cnt, bool with_x) {
+            const int s = it % p.stages;
+            mbar_wait(full_bar(s), (it / p.stages) & 1);
+            uint8_t* base = smem_gen + (size_t)s * stage_bytes;
+            const int a_vec = cnt * (int)(kABytes / 16);
+#pragma unroll 4
+            for (int v = st; v < a_vec; v += kSplitThreads) {
+                const float4 x = *reinterpret_cast<const float4*>(base + 16 * v);
+                *reinterpret_cast<float4*>(base + half_stage + 16 * v) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+            }
+            if (with_x) {
+                const int b_vec = cnt * (int)(b_bytes / 16);
+                for (int v = st; v < b_vec; v += kSplitThreads) {
+                    const float4 x = *reinterpret_cast<const float4*>(base + stage_b_off + 16 * v);
+                    *reinterpret_cast<float4*>(base + half_stage + stage_b_off + 16 * v) =
+                        make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(split_bar(s));
+            ++it;
+        };
+        if (p.do_fwd)
+            for (int l = 1; l <= L; ++l) {
+                const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
+                for (int kb0 = 0; kb0 < nkb; kb0 += p.kps) derive(min(p.kps, nkb - kb0), l == 1);
+            }
+        if (p.do_bwd)
+            for (int l = L; l >= bwd_lo; --l) {
+                const int nkb = (p.layers[l - 1].out + (int)kBlockK - 1) / (int)kBlockK;
+                for (int kb0 = 0; kb0 < nkb; kb0 += p.kps) derive(min(p.kps, nkb - kb0), false);
+            }
     } else {
         // ============================================================ epilogue warps
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
@@ -549,7 +557,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
-    if constexpr (MC) chain_cluster_sync();                  // peers may still signal my ring barriers until they are done too
 }
 
 // =========================================================================== host side
@@ -573,7 +580,7 @@ bool chain_budget(int mb_rows, bool split, int* kps_out, int* stages_out, int* s
     if (stages > 8) stages = 8;
     *kps_out = kps;
     *stages_out = stages;
-    *smem_bytes_out = stages * stage_bytes + (split ? 4 : 2) * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
+    *smem_bytes_out = stages * stage_bytes + (split ? 4 : 2) * abuf_bytes + 1024 + 8 * (3 * stages + 3) + 16 + scratch_bytes;
     return true;
 }
 
@@ -594,27 +601,19 @@ bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out
 }
 
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       const float* W_lo, const float* x_lo, bool multicast) {
+                       int split_mode, const float* W_lo, const float* x_lo) {
     *plan = ChainPlan{};
     ChainParams& p = plan->p;
     p = params;
     const int L = p.n_layers;
     p.n_pad = (p.mb_rows + 15) / 16 * 16;
-    p.split = (W_lo != nullptr) ? 1 : 0;
+    p.split = split_mode != 0 ? 1 : 0;
+    p.derive = split_mode == 2 ? 1 : 0;
+    if (split_mode == 1 && W_lo == nullptr) return "chain_plan: split_mode 1 needs the W_lo arena";
     const int nmaps = 2 * L + 1;
-    // multicast variant: clusters of 4 micro-batch CTAs; needs quarter-tile (32-row) maps of the forward weights
-    const bool mc = multicast && n_mubatches >= 4 && n_mubatches % 4 == 0;
-    p.mc_base = mc ? nmaps * (p.split ? 2 : 1) : 0;
-    plan->cluster = mc ? 4 : 1;
-    std::vector<CUtensorMap> host(nmaps * (p.split ? 2 : 1) + (mc ? L * (p.split ? 2 : 1) : 0));
-    if (mc)
-        for (int half = 0; half < (p.split ? 2 : 1); ++half)
-            for (int l = 0; l < L; ++l) {
-                const ChainLayer& ly = p.layers[l];
-                if (const char* e = make_tmap_k(&host[p.mc_base + half * L + l], (half ? W_lo : p.W) + ly.w_off, ly.in, ly.out, ly.ldw, 32))
-                    return e;
-            }
-    for (int half = 0; half < (p.split ? 2 : 1); ++half) {
+    const int halves = (split_mode == 1) ? 2 : 1;            // derive mode loads no twins: no maps for them
+    std::vector<CUtensorMap> host(nmaps * halves);
+    for (int half = 0; half < halves; ++half) {
         const float* Wb = half ? W_lo : p.W;
         const float* xb = half ? x_lo : x;
         for (int l = 0; l < L; ++l) {
@@ -651,26 +650,13 @@ void chain_plan_free(ChainPlan* plan) {
 cudaError_t chain_configure() {
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(mlp_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
-    if (plan.cluster > 1) {                                  // multicast variant: clusters of 4 micro-batch CTAs
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(plan.grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = plan.smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = plan.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (plan.p.split) return cudaLaunchKernelEx(&cfg, mlp_chain_kernel<true, true>, plan.p);
-        return cudaLaunchKernelEx(&cfg, mlp_chain_kernel<false, true>, plan.p);
-    }
-    if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.p.split && plan.p.derive) mlp_chain_kernel<true, true><<<plan.grid, kThreadsDerive, plan.smem_bytes, stream>>>(plan.p);
+    else if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     else mlp_chain_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     return cudaGetLastError();
 }

@@ -36,12 +36,9 @@ static constexpr uint32_t kPanelBytes = 32 * 128;       // MN-major panel: 32 k-
 // k-blocks; every CTA writes its raw fp32 accumulator tile to a workspace and the LAST CTA to arrive at the
 // tile's counter sums the partials in split order (deterministic) and runs the fused epilogue.  Nobody
 // waits for anybody, so the CTAs of a tile need not be co-resident.
-// WLO (WGRAD with the SGD update fused, fp32-equivalent mode): after the -lr*dW tile has been reduce-added into
-// W, the same CTA reads the updated tile back from L2 and writes its lo twin (W - trunc_tf32(W)), which removes
-// the arena-wide split kernel (and its graph edge) from the end of every step.
 // The body is shared by the one-GEMM-per-launch kernels below and by the grouped weight-gradient kernel (several
 // layers' tiles in ONE launch, tensor maps and parameters read from a device table).
-template <int MODE, bool SPLITK, bool WLO>
+template <int MODE, bool SPLITK>
 __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, const GemmParams& p, const int bx,
                                              const int by, const int bz) {
@@ -351,7 +348,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                 }
                 tma_store_commit();
                 tma_store_wait_all();
-                if constexpr (WLO) asm volatile("fence.proxy.async.global;" ::: "memory");   // async-proxy writes -> generic reads
             }
             // TMA stores clip the inner dimension at 16-byte granularity (measured on B200: with
             // in % 4 != 0 the partially valid last chunk is written in full), i.e. the bias slot in
@@ -367,26 +363,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                     *dbp = p.accumulate ? (*dbp + dbsum) : dbsum;
                 }
             }
-            if constexpr (WLO) {
-                // the reduce-add retired (wait_group 0 by warp 2 lane 0, then the bar.sync above): re-read the tile
-                // through L2 (.cg) with all 128 epilogue threads, coalesced, and refresh its lo twin
-                const int t = (int)threadIdx.x - 64;
-                const int f4_per_row = p.block_n / 4;
-                for (int idx = t; idx < (int)kBlockM * f4_per_row; idx += 128) {
-                    const int r = idx / f4_per_row, c = (idx - r * f4_per_row) * 4;
-                    const int mm = m0 + r, nn = n0 + c;
-                    if (mm >= p.m_total || nn >= p.n_total) continue;
-                    const float* src = p.W + (size_t)mm * p.ldw + nn;
-                    float* dst = p.W_lo + (size_t)mm * p.ldw + nn;
-                    if (nn + 3 < p.n_total) {
-                        const float4 w = __ldcg(reinterpret_cast<const float4*>(src));
-                        *reinterpret_cast<float4*>(dst) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
-                    } else {
-                        for (int j = 0; j < 4; ++j)
-                            if (nn + j < p.n_total) dst[j] = tf32_lo(__ldcg(src + j));
-                    }
-                }
-            }
         }
         tc_fence_before();
     }
@@ -398,22 +374,21 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
     }
 }
 
-template <int MODE, bool SPLITK = false, bool WLO = false>
+template <int MODE, bool SPLITK = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
-    tc_gemm_body<MODE, SPLITK, WLO>(tmA, tmB, tmC, tmAlo, tmBlo, p, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    tc_gemm_body<MODE, SPLITK>(tmA, tmB, tmC, tmAlo, tmBlo, p, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // ---- grouped weight-gradient launch: the tiles of SEVERAL layers' WGRAD GEMMs in one grid (one table entry per CTA).
-// Removes the fork / join of one graph node per layer from the end of a step; combined with WLO (no split kernel)
-// and the zero-copy loss the whole training step is two graph nodes: chain kernel -> grouped wgrad.
-template <bool WLO>
+// Removes the fork / join of one graph node per layer from the end of a step; with the zero-copy loss and the chain
+// kernel deriving its lo twins on chip the whole fp32 training step is two graph nodes: chain kernel -> grouped wgrad.
 __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_group_kernel(const GemmGroupEntry* __restrict__ entries) {
     const GemmGroupEntry& e = entries[blockIdx.x];
     const GemmParams p = e.p;                      // private copy: the body reads these fields in every loop
-    tc_gemm_body<GEMM_WGRAD, false, WLO>(e.tmA, e.tmB, e.tmC, e.tmAlo, e.tmBlo, p, e.bx, e.by, 0);
+    tc_gemm_body<GEMM_WGRAD, false>(e.tmA, e.tmB, e.tmC, e.tmAlo, e.tmBlo, p, e.bx, e.by, 0);
 }
 
 // =========================================================================== host side
@@ -594,12 +569,10 @@ const char* gemm_group_plan(GemmGroupPlan* out, const GemmPlan* plans, int n_pla
     if (n_plans < 1) return "gemm_group_plan: no plans";
     std::vector<GemmGroupEntry> host;
     int smem = 0;
-    const bool wlo = plans[0].p.W_lo != nullptr && plans[0].p.fuse_sgd;
     for (int i = 0; i < n_plans; ++i) {
         const GemmPlan& g = plans[i];
         if (g.mode != GEMM_WGRAD) return "gemm_group_plan: only weight-gradient GEMMs can be grouped";
         if (g.p.k_splits > 1) return "gemm_group_plan: split-K plans cannot be grouped";
-        if ((g.p.W_lo != nullptr && g.p.fuse_sgd) != wlo) return "gemm_group_plan: mixed lo-twin modes";
         if (g.smem_bytes > smem) smem = g.smem_bytes;
         for (unsigned by = 0; by < g.grid.y; ++by)
             for (unsigned bx = 0; bx < g.grid.x; ++bx) {
@@ -616,7 +589,7 @@ const char* gemm_group_plan(GemmGroupPlan* out, const GemmPlan* plans, int n_pla
         cudaFree(dev);
         return "gemm_group_plan: table upload failed";
     }
-    out->entries_dev = dev; out->n = (int)host.size(); out->smem_bytes = smem; out->wlo = wlo ? 1 : 0; out->n_gemms = n_plans;
+    out->entries_dev = dev; out->n = (int)host.size(); out->smem_bytes = smem; out->n_gemms = n_plans;
     return nullptr;
 }
 
@@ -637,9 +610,7 @@ cudaError_t gemm_configure() {
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_WGRAD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_wgrad_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_wgrad_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_gemm_kernel<GEMM_DGRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)) != cudaSuccess) return e;
     g_configured = true;
@@ -651,8 +622,7 @@ cudaError_t gemm_group_launch(const GemmGroupPlan& plan, cudaStream_t stream) {
         cudaError_t e = gemm_configure();
         if (e != cudaSuccess) return e;
     }
-    if (plan.wlo) tc_wgrad_group_kernel<true><<<plan.n, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev);
-    else tc_wgrad_group_kernel<false><<<plan.n, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev);
+    tc_wgrad_group_kernel<<<plan.n, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev);
     g_launches.fetch_add(plan.n_gemms, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -666,13 +636,6 @@ static cudaError_t launch_mode(const GemmPlan& plan, cudaStream_t stream) {
     if constexpr (MODE != GEMM_WGRAD) {
         if (plan.p.k_splits > 1) {
             tc_gemm_kernel<MODE, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            return cudaGetLastError();
-        }
-    }
-    if constexpr (MODE == GEMM_WGRAD) {
-        if (plan.p.W_lo != nullptr && plan.p.fuse_sgd) {
-            tc_gemm_kernel<MODE, false, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmAlo, plan.tmBlo, plan.p);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return cudaGetLastError();
         }

@@ -260,7 +260,6 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.inv_batch = 1.0f / (float)cfg_.global_batch;
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
-    cp.mc_base = 0;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {
             CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
@@ -270,10 +269,11 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
         cp.dbg = chain_dbg_;
     }
     ChainPlan plan;
-    // opt-in (SSB_CHAIN_MC=1, awaiting hardware validation): clusters of 4 micro-batch CTAs multicast the weight tiles
-    const bool mc = getenv("SSB_CHAIN_MC") != nullptr && atoi(getenv("SSB_CHAIN_MC")) > 0;
-    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, cfg_.split ? W_lo_ : nullptr,
-                                 cfg_.split ? act_lo_all_[0] : nullptr, mc);
+    // 3xTF32: the lo twins of the streamed weight / input tiles are derived on chip (chain_derive_), or loaded from the
+    // W_lo arena and the staged X_lo (SSB_CHAIN_NO_DERIVE=1: the round-1 path, kept for A/B measurements)
+    const int split_mode = !cfg_.split ? 0 : (chain_derive_ ? 2 : 1);
+    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, split_mode,
+                                 split_mode == 1 ? W_lo_ : nullptr, split_mode == 1 ? act_lo_all_[0] : nullptr);
     if (err) throw std::runtime_error(std::string("PipeEngine chain plan: ") + err);
     chain_plans_.push_back(plan);
     Op op;
@@ -322,6 +322,10 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         for (int l = 0; l < nl; ++l) { cl[l].in = cfg_.layers[l].in; cl[l].out = cfg_.layers[l].out; }
         chain_ok_ = L_ >= 1 && L_ <= kChainMaxLayers && !getenv("SSB_NO_CHAIN") &&
                     chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0, cfg_.split != 0);
+        // With the chain kernel deriving lo twins on chip nothing reads the W_lo arena any more (the weight-gradient
+        // GEMMs read the lo twins of activations and gradients only): no refresh kernel after the optimizer step.
+        chain_derive_ = chain_ok_ && cfg_.split && !(getenv("SSB_CHAIN_NO_DERIVE") && atoi(getenv("SSB_CHAIN_NO_DERIVE")) > 0);
+        w_lo_needed_ = cfg_.split && !chain_derive_;
     }
     if (pp_ctx_) {
         // peer-memory transport: the neighbours write straight into my receive slots, which therefore live in the
@@ -356,7 +360,7 @@ void PipeEngine::plan_per_mubatch() {
     const bool first = cfg_.is_first, last = cfg_.is_last;
     std::vector<bool> started(streams_.size(), false);
     started[0] = true;
-    if (cfg_.split && !cfg_.training) {      // inference: weights are updated by the training engine between calls
+    if (w_lo_needed_ && !cfg_.training) {      // inference: weights are updated by the training engine between calls
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -672,7 +676,7 @@ void PipeEngine::plan_per_mubatch() {
         cr.b = cfg_.training ? reinterpret_cast<float*>(pp_ctx_->next_dz_credit()) : nullptr;
         ops_.push_back(cr);
     }
-    if (cfg_.split && cfg_.training) {       // weights changed: refresh their lo twin for the next step
+    if (w_lo_needed_ && cfg_.training) {     // weights changed: refresh their lo twin for the next step
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -711,7 +715,7 @@ void PipeEngine::build_coalesced() {
     auto use = [&](int s) { if (!started[s]) { emit_wait(s, ev_begin); started[s] = true; } };
     auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
 
-    if (cfg_.split && !cfg_.training) {      // weights are updated by the training engine between calls
+    if (w_lo_needed_ && !cfg_.training) {      // weights are updated by the training engine between calls
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -758,9 +762,6 @@ void PipeEngine::build_coalesced() {
     }
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
-    // opt-in (SSB_FUSE_WLO=1, awaiting hardware validation): the SGD-fused wgrad kernels also refresh the lo twin
-    // of the weights, so the arena-wide split kernel at the end of the step disappears
-    const bool fuse_wlo = fuse && cfg_.split && getenv("SSB_FUSE_WLO") != nullptr && atoi(getenv("SSB_FUSE_WLO")) > 0;
     // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
     // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
     // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
@@ -824,7 +825,6 @@ void PipeEngine::build_coalesced() {
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
-        if (fuse_wlo) g.p.W_lo = W_lo_ + ls.offset;       // the epilogue refreshes the lo twin of its own tile
         if (group_wgrad) { grouped.push_back(g); continue; }   // launched together after the loop
         add_gemm(g, w, l);
         if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
@@ -859,7 +859,7 @@ void PipeEngine::build_coalesced() {
     }
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
-    if (cfg_.split && !fuse_wlo) {           // weights changed: refresh their lo twin for the next step
+    if (w_lo_needed_) {                      // weights changed: refresh their lo twin for the next step
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -886,11 +886,11 @@ void PipeEngine::finish_build() {
     // kernel attributes are configured up front (never inside a capture); communicators are
     // warmed up by their creator.  No eager pass here: a training step mutates the weights.
     CUDA_CHECK(gemm_configure());
-    if (cfg_.split) {                        // first step needs a valid lo twin of the initial weights
+    if (w_lo_needed_) {                      // first step needs a valid lo twin of the initial weights
         CUDA_CHECK(launch_split_lo(W_, W_lo_, arena_numel_, streams_[0]));
         CUDA_CHECK(cudaStreamSynchronize(streams_[0]));
-        ++kernels_per_step_;                 // + the staged-input split issued on the copy stream every step
     }
+    if (cfg_.split && cfg_.is_first) ++kernels_per_step_;   // + the staged-input split issued on the copy stream every step
     if (!chain_plans_.empty()) CUDA_CHECK(chain_configure());
     if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
     comm_timing_ = getenv("SSB_COMM_TIMING") != nullptr;   // needs timing events between ops: eager plan walk

@@ -160,6 +160,8 @@ private:
     std::vector<float*> act_lo_all_, dz_lo_all_; // lo twins (split mode)
     std::vector<std::vector<float*>> act_lo_, dz_lo_;
     float* W_lo_ = nullptr;
+    bool chain_derive_ = false;      // 3xTF32 chain kernel derives lo twins on chip
+    bool w_lo_needed_ = false;       // something reads the W_lo arena (per-layer fwd / dgrad kernels, or the NO_DERIVE chain)
     float* x_lo_sets_[2] = {nullptr, nullptr};
     GemmLo lo_fwd(int l, int mu) const;
     GemmLo lo_dgrad(int l, int mu) const;

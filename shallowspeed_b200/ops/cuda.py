@@ -99,17 +99,15 @@ def linear_dgrad(dz, weight, mask=None, out=None, precision=None, k_splits=0):
     return dx
 
 
-def linear_wgrad(dz, x, grad_w, accumulate=False, grad_b=None, weight=None, lr=0.0, fuse_sgd=False, precision=None,
-                 weight_lo_out=None):
+def linear_wgrad(dz, x, grad_w, accumulate=False, grad_b=None, weight=None, lr=0.0, fuse_sgd=False, precision=None):
     """grad_w[out, in] (+)= dz^T @ x ; grad_b (+)= colsum(dz).  With ``fuse_sgd`` the update goes straight into
-    ``weight``; ``weight_lo_out`` (experimental) additionally receives the lo twin of the updated weights."""
+    ``weight`` (TMA reduce-add of -lr * dW)."""
     dz, x = as_tma(dz), as_tma(x)
     b, bstride = _bias_arg(grad_b, dz.size(1))
     if _split(precision):
-        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), lo_twin(dz), lo_twin(x),
-                        weight_lo_out)
+        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), lo_twin(dz), lo_twin(x))
     else:
-        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), None, None, weight_lo_out)
+        _C.linear_wgrad(dz, x, grad_w, bool(accumulate), b, bstride, weight, float(lr), bool(fuse_sgd), None, None)
     return grad_w
 
 

@@ -1,22 +1,14 @@
-"""Opt-in kernels written after the round's GPU budget was spent (split-K GEMMs, lo-twin-refreshing wgrad, multicast
-chain kernel).  NOT collected by default (file name): tests/test_gpu_zz_aux.py runs each group in its OWN python process,
-so a device trap in one experimental kernel cannot poison the CUDA context of anything else.
-
-    python -m pytest tests/experimental_cases.py -q            # run them directly on a GPU box
-"""
+"""Kernel variants that were validated on B200 in round 2 (first written without hardware at the end of round 1):
+split-K FWD / DGRAD GEMMs, zero-copy loss read-back, grouped weight-gradient launch, and the chain kernel that derives
+its 3xTF32 lo twins on chip.  Every variant is compared against the path it replaces: bit for bit where the MMAs and
+their order are unchanged, against an fp64 oracle otherwise.  Switches live in ``shallowspeed_b200/tuning.json``; an
+explicit environment variable always wins, which is how these tests pin each side of a comparison."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
 SIZES = [784, 128, 127, 126, 125, 124, 123, 10]
-
-
-# ---------------------------------------------------------------------------------------------------------
-# Experimental: split-K variant of the FWD / DGRAD GEMMs for wide layers (opt-in: k_splits= / SSB_SPLITK).
-# Written after the round's GPU budget was spent, so these are the first executions on hardware;
-# each group runs in its own process (tests/test_gpu_zz_aux.py).
-# ---------------------------------------------------------------------------------------------------------
 
 
 def _report(got, ref, tol):
@@ -68,14 +60,16 @@ def test_splitk_dgrad_with_relu_mask_matches_oracle(precision, tol):
     assert (got - ref).abs().max().item() <= bound, _report(got, ref, bound)
 
 
-def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
+def test_engine_splitk_trains_like_the_plain_kernels(monkeypatch):
     from shallowspeed_b200.dataset import synthetic_mnist
     from shallowspeed_b200.parallel.engine import Trainer
 
     sizes = [784, 2048, 2048, 10]
     x, y = synthetic_mnist(n=256)
     xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_SPLITK", "0")
     base = Trainer(sizes, lr=0.05, seed_mode="index")
+    assert "splitk_gemms=0" in base.engine.describe()
     ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(2)]
     monkeypatch.setenv("SSB_SPLITK", "1")
     tr = Trainer(sizes, lr=0.05, seed_mode="index")
@@ -85,70 +79,7 @@ def test_engine_splitk_optin_trains_like_the_default(monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Experimental: SGD-fused wgrad that also refreshes the lo twin of the updated weight tile (SSB_FUSE_WLO=1).
-# ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,k,n", [(32, 128, 127), (128, 784, 128), (32, 123, 10), (64, 300, 200)])
-def test_wgrad_fused_sgd_refreshes_weight_lo_twin(rows, k, n):
-    from shallowspeed_b200.ops import cuda as K
-
-    torch.manual_seed(0)
-    lr = 0.05
-    dz, x = torch.randn(rows, n, device="cuda"), torch.randn(rows, k, device="cuda")
-    ld = (k + 1 + 7) // 8 * 8
-    W, G = torch.randn(n, ld, device="cuda"), torch.zeros(n, ld, device="cuda")
-    W_ref = W.clone()
-    stale = K.lo_twin(W.clone()[:, :k])                    # lo twin of the OLD weights: what a stale read-back would produce
-    W_lo = torch.full((n, ld), 7.0, device="cuda")        # sentinel: every weight element must be rewritten
-    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W_ref[:, :k], lr=lr, fuse_sgd=True, precision="fp32")
-    K.linear_wgrad(dz, x, G[:, :k], accumulate=False, grad_b=G[:, k], weight=W[:, :k], lr=lr, fuse_sgd=True, precision="fp32",
-                   weight_lo_out=W_lo[:, :k])
-    assert torch.equal(W, W_ref), "update changed: " + _report(W, W_ref, 0.0)
-    want = K.lo_twin(W[:, :k])
-    assert torch.equal(W_lo[:, :k], want), ("lo twin of the NEW weights, bit for bit: " + _report(W_lo[:, :k], want, 0.0) +
-                                            f"; sentinel survivors {int((W_lo[:, :k] == 7.0).sum())}; equals stale twin: {torch.equal(W_lo[:, :k], stale)}")
-    assert bool((W_lo[:, k:] == 7.0).all())                # bias slot / padding untouched
-
-
-def test_engine_fused_weight_lo_optin_is_bitwise_identical(monkeypatch):
-    from shallowspeed_b200.dataset import synthetic_mnist
-    from shallowspeed_b200.parallel.engine import Trainer
-
-    x, y = synthetic_mnist(n=128 * 4)
-    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    base = Trainer(SIZES, lr=0.1)
-    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
-    monkeypatch.setenv("SSB_FUSE_WLO", "1")
-    tr = Trainer(SIZES, lr=0.1)
-    assert int(tr.engine.kernels_per_step()) == int(base.engine.kernels_per_step()) - 1   # the split kernel is gone
-    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
-    assert got == ref                                      # same products, same order: identical losses
-    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
-
-
-# ---------------------------------------------------------------------------------------------------------
-# Experimental: chain kernel with a 4-CTA cluster sharing the weight stream through TMA multicast (SSB_CHAIN_MC=1).
-# ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision", ["tf32", "fp32"])
-@pytest.mark.parametrize("n_mu", [4, 8])
-def test_chain_multicast_cluster_is_bitwise_identical(monkeypatch, precision, n_mu):
-    from shallowspeed_b200.dataset import synthetic_mnist
-    from shallowspeed_b200.parallel.engine import Trainer
-
-    x, y = synthetic_mnist(n=128 * 3)
-    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    base = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision=precision)
-    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(3)]
-    monkeypatch.setenv("SSB_CHAIN_MC", "1")
-    tr = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision=precision)
-    assert tr.engine.uses_chain()
-    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(3)]
-    assert got == ref                                      # same MMAs in the same order: identical losses
-    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
-
-
-
-# ---------------------------------------------------------------------------------------------------------
-# Experimental: loss values stored straight into pinned host memory (SSB_LOSS_ZEROCOPY=1), no D2H copy node.
+# Loss values stored straight into pinned host memory (SSB_LOSS_ZEROCOPY=1), no D2H copy node.
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", [{}, {"SSB_NO_CHAIN": "1"}, {"SSB_NO_COALESCE": "1"}])
 def test_loss_zero_copy_readback_matches(monkeypatch, env):
@@ -159,7 +90,9 @@ def test_loss_zero_copy_readback_matches(monkeypatch, env):
         monkeypatch.setenv(k, v)
     x, y = synthetic_mnist(n=128 * 4)
     xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_LOSS_ZEROCOPY", "0")
     base = Trainer(SIZES, lr=0.1)
+    assert "loss_d2h" in base.engine.plan_text(0)
     ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
     monkeypatch.setenv("SSB_LOSS_ZEROCOPY", "1")
     tr = Trainer(SIZES, lr=0.1)
@@ -173,7 +106,7 @@ def test_loss_zero_copy_readback_matches(monkeypatch, env):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Experimental: all layers' weight-gradient tiles in ONE launch (SSB_WGRAD_GROUP=1); with the lo-twin-refreshing
+# All layers' weight-gradient tiles in ONE launch (SSB_WGRAD_GROUP=1); with the lo-twin-refreshing
 # epilogue and the zero-copy loss the whole step is two graph nodes.
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["tf32", "fp32"])
@@ -183,7 +116,9 @@ def test_wgrad_group_launch_is_bitwise_identical(monkeypatch, precision):
 
     x, y = synthetic_mnist(n=128 * 4)
     xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_WGRAD_GROUP", "0")
     base = Trainer(SIZES, lr=0.1, precision=precision)
+    assert "wgrad_group" not in base.engine.plan_text(0)
     ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
     monkeypatch.setenv("SSB_WGRAD_GROUP", "1")
     tr = Trainer(SIZES, lr=0.1, precision=precision)
@@ -194,24 +129,87 @@ def test_wgrad_group_launch_is_bitwise_identical(monkeypatch, precision):
     assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
 
 
-def test_two_node_step_all_optins_together(monkeypatch):
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_default_training_step_is_two_graph_nodes(monkeypatch, precision):
+    """chain kernel -> grouped wgrad + SGD, nothing else: no loss copy node, no weight-split kernel (fp32: the chain
+    kernel derives its lo twins on chip), no per-layer fork / join."""
     from shallowspeed_b200.dataset import synthetic_mnist
     from shallowspeed_b200.parallel.engine import Trainer
     from shallowspeed_b200.parallel.plan_check import check_plan
 
     x, y = synthetic_mnist(n=128 * 4)
     xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
-    base = Trainer(SIZES, lr=0.1)
+    for k in ("SSB_WGRAD_GROUP", "SSB_LOSS_ZEROCOPY", "SSB_CHAIN_NO_DERIVE"):
+        monkeypatch.setenv(k, "0")
+    base = Trainer(SIZES, lr=0.1, precision=precision)
     ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
-    for k in ("SSB_WGRAD_GROUP", "SSB_FUSE_WLO", "SSB_LOSS_ZEROCOPY"):
+    for k in ("SSB_WGRAD_GROUP", "SSB_LOSS_ZEROCOPY"):
         monkeypatch.setenv(k, "1")
-    tr = Trainer(SIZES, lr=0.1)
+    tr = Trainer(SIZES, lr=0.1, precision=precision)
     stats = check_plan(tr.engine.plan_text(0))
-    assert stats["kernels_and_copies"] == 2, tr.engine.plan_text(0)      # chain kernel + grouped wgrad, nothing else
+    assert stats["kernels_and_copies"] == 2, tr.engine.plan_text(0)
+    assert int(tr.engine.graph_nodes()) == 2
     got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
     assert got == ref and torch.equal(tr.model.arena.weights, base.model.arena.weights)
-    # ... and with the multicast chain kernel on top (only meaningful once test_chain_multicast_* passes on its own)
-    monkeypatch.setenv("SSB_CHAIN_MC", "1")
-    tr2 = Trainer(SIZES, lr=0.1)
-    got2 = [tr2.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
-    assert got2 == ref, "two-node step is fine, the multicast chain kernel on top of it is not"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3xTF32 chain kernel: lo twins of the streamed weight / input tiles derived in shared memory by four extra warps
+# (default) versus loaded from the W_lo arena / staged X_lo (SSB_CHAIN_NO_DERIVE=1, the round-1 path).  The operands of
+# every MMA are the same numbers in the same order, so training must be bit-identical - for the coalesced plan (all
+# micro-batches in one launch), for other micro-batch sizes / ring depths, and for the per-micro-batch plan pipeline
+# stages use (forward-only and backward-only launches of the same kernel).
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_mu,env", [(4, {}), (8, {}), (1, {}), (2, {"SSB_NO_COALESCE": "1"}), (4, {"SSB_NO_COALESCE": "1"})])
+def test_chain_on_chip_lo_twins_are_bitwise_identical_to_loaded_twins(monkeypatch, n_mu, env):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_CHAIN_NO_DERIVE", "1")
+    base = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision="fp32")
+    assert base.engine.uses_chain() and "split_lo" in base.engine.plan_text(0)
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_CHAIN_NO_DERIVE", "0")
+    tr = Trainer(SIZES, lr=0.1, n_mubatches=n_mu, precision="fp32")
+    assert tr.engine.uses_chain() and "split_lo" not in tr.engine.plan_text(0)      # nobody reads the W_lo arena any more
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert got == ref, (got, ref)
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
+
+
+def test_chain_on_chip_lo_twins_inference_engine(monkeypatch):
+    """validation engine (forward-only chain launch) right after training steps changed the weights: with the derived
+    twins there is no stale W_lo to refresh"""
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 2)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    tr = Trainer(SIZES, lr=0.1, precision="fp32")
+    tr.step(xh[:128], yh[:128])
+    tr.step(xh[128:], yh[128:])
+    tr.synchronize()
+    # fp64 forward of the trained weights on the host
+    h = torch.from_numpy(x[:128]).double()
+    lins = tr.model.linears
+    for i, lin in enumerate(lins):
+        h = h @ lin._params["W"].data.cpu().double().T + lin._params["b"].data.cpu().double().reshape(1, -1)
+        if lin.activation is not None:
+            h = torch.relu(h)
+    z = h - h.max()
+    ref = torch.exp(z) / (torch.exp(z).sum(1, keepdim=True) + 1e-7)
+    from shallowspeed_b200.parallel.engine import NativeWorker
+    from shallowspeed_b200.pipe import InferenceSchedule
+
+    class _Shape:
+        mubatch_size = 128
+
+    vw = NativeWorker(None, None, tr.model, _Shape(), None, precision="fp32", share=tr.worker)
+    eng = vw.step_from(InferenceSchedule(1, 1, 0), xh[:128], yh[:128])
+    eng.synchronize()
+    got = eng.probs(0).cpu().double()
+    assert float((got - ref).abs().max()) < 1e-5

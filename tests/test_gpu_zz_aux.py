@@ -48,22 +48,3 @@ def test_lowered_plans_pass_the_self_check(monkeypatch, env):
     for s in (0, 1):
         stats = check_plan(tr.engine.plan_text(s))
         assert stats["kernels_and_copies"] >= 3 and stats["ops"] == len(tr.engine.plan_text(s).splitlines())
-
-
-# ---------------------------------------------------------------------------------------------------------
-# Experimental opt-in kernels (tests/experimental_cases.py): one isolated python process per group, so a device
-# trap in a kernel that has never run on hardware cannot poison this process.  Non-strict xfail: the outcome is
-# information for the next round, not a gate.
-# ---------------------------------------------------------------------------------------------------------
-@pytest.mark.xfail(strict=False, reason="opt-in kernels written without GPU access: first run on hardware")
-@pytest.mark.parametrize("group", ["splitk", "weight_lo", "chain_multicast", "loss_zero_copy", "wgrad_group_launch or two_node_step"])
-def test_experimental_group_in_isolated_process(group):
-    import os
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "experimental_cases.py"), "-k", group, "-q", "-x",
-                        "-p", "no:cacheprovider"], cwd=root, capture_output=True, text=True, timeout=300)
-    tail = (r.stdout or "")[-3000:] + (r.stderr or "")[-1500:]
-    assert r.returncode == 0, tail
