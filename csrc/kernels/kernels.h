@@ -51,7 +51,11 @@ struct GemmParams {
     int k_splits;                 // 0 / 1 = off
     float* partial;
     unsigned int* tile_counter;   // zero before the first launch; re-armed by the kernel
-    // WGRAD + fuse_sgd in fp32-equivalent mode (opt-in): also refresh the lo twin of the updated weight tile
+    // WGRAD launched CONCURRENTLY with the kernel that produces its operands (the layer-chain kernel): the TMA producer
+    // first waits until *gate_flag >= gate_mult * *gate_step (device counters; release/acquire at gpu scope).
+    const uint32_t* gate_flag;    // nullptr = not gated
+    const uint32_t* gate_step;
+    uint32_t gate_mult;
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
@@ -183,6 +187,8 @@ struct ChainParams {
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
     int derive;                      // split mode: lo twins of the streamed tiles are derived on chip (no W_lo / X_lo loads)
+    uint32_t* ready;                 // optional [n_layers + 1] device counters: every epilogue warp of every CTA adds 1 to
+                                     // ready[l] once its part of dz[l] (and everything it wrote before) is globally visible
     unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only
 };
 struct ChainPlan {

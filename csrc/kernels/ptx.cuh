@@ -225,6 +225,26 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t target)
         if (clock64() - t0 > SSB_SPIN_LIMIT_CYCLES) __trap();
     }
 }
+// ---- gpu-scope counters: producer kernel -> concurrently running consumer kernel on the same device
+__device__ __forceinline__ void red_add_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_counter_ge_gpu(const uint32_t* p, uint32_t target) {
+    if (static_cast<int32_t>(ld_acquire_gpu(p) - target) >= 0) return;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_gpu(p) - target) < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > SSB_SPIN_LIMIT_CYCLES) __trap();
+    }
+}
+// generic-proxy global writes (of another kernel, observed through an acquire) -> this thread's TMA (async proxy) reads
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"

@@ -260,6 +260,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.inv_batch = 1.0f / (float)cfg_.global_batch;
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
+    cp.ready = (gate_on_ && do_bwd && do_fwd) ? gate_ready_ : nullptr;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {
             CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
@@ -721,6 +722,22 @@ void PipeEngine::build_coalesced() {
         ops_.push_back(sp);
     }
     const bool chain = chain_ok_;
+    // Gated weight-gradient wave (SSB_WGRAD_GATE, with the grouped launch): the grouped wgrad + SGD kernel is forked at
+    // the START of the step next to the chain kernel instead of behind it.  The chain kernel's epilogue warps count up a
+    // per-layer device counter when dz[l] is globally visible; the CTAs of layer l wait for ready[l-1] (dz[l] final AND
+    // the dgrad that reads W_l retired - W_l is updated in place) before their first TMA load.  Only the last layers'
+    // tiles remain behind the chain kernel; the launch gap and the rest of the wave hide behind the backward pass.
+    const bool group_env = getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
+    gate_on_ = chain && cfg_.training && cfg_.dp_mode == 0 && group_env && getenv("SSB_WGRAD_GATE") != nullptr &&
+               atoi(getenv("SSB_WGRAD_GATE")) > 0;
+    if (gate_on_ && gate_ready_ == nullptr) {
+        uint32_t* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, 256));
+        CUDA_CHECK(cudaMemset(p, 0, 256));
+        owned_.push_back(p);
+        gate_ready_ = p;              // [0 .. L] per-layer counters, [32] step counter of this engine
+        gate_step_ = p + 32;
+    }
     if (chain) {
         // forward + loss head (+ whole dgrad chain when training) of every micro-batch in ONE launch
         add_chain(0, 0, M, true, true, cfg_.training != 0);
@@ -765,7 +782,7 @@ void PipeEngine::build_coalesced() {
     // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
     // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
     // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
-    const bool group_wgrad = (fuse || cfg_.dp_mode == 3) && chain && getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
+    const bool group_wgrad = (fuse || cfg_.dp_mode == 3) && chain && group_env;
     std::vector<GemmPlan> grouped;
     int ev_bump = -1;
     if (fused_dp) {
@@ -825,7 +842,15 @@ void PipeEngine::build_coalesced() {
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
-        if (group_wgrad) { grouped.push_back(g); continue; }   // launched together after the loop
+        if (group_wgrad) {                                  // launched together after the loop
+            if (gate_on_) {
+                g.p.gate_flag = gate_ready_ + (l >= 2 ? l - 1 : 1);
+                g.p.gate_step = gate_step_;
+                g.p.gate_mult = 8u * (uint32_t)M;          // 8 epilogue warps per chain CTA, one CTA per micro-batch
+            }
+            grouped.push_back(g);
+            continue;
+        }
         add_gemm(g, w, l);
         if (cfg_.dp_mode == 1 && cfg_.dp_size > 1) {
             const int ev_g = emit_record(w);
@@ -842,6 +867,14 @@ void PipeEngine::build_coalesced() {
         group_plans_.push_back(gp);
         Op go;
         go.kind = OP_WGRAD_GROUP; go.stream = 0; go.gemm = (int)group_plans_.size() - 1;
+        if (gate_on_) {                                     // own branch, forked at the begin of the step
+            const int gs = sw(0);
+            use(gs);
+            Op bs;
+            bs.kind = OP_BUMP_STEP; bs.stream = gs;
+            ops_.push_back(bs);
+            go.stream = gs;
+        }
         ops_.push_back(go);
     }
     if (!fuse && !fused_dp) {
@@ -878,7 +911,7 @@ void PipeEngine::finish_build() {
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
             op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD ||
             op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT || op.kind == OP_PP_CREDIT || op.kind == OP_PP_BUMP ||
-            op.kind == OP_WGRAD_GROUP)
+            op.kind == OP_WGRAD_GROUP || op.kind == OP_BUMP_STEP)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -961,6 +994,7 @@ void PipeEngine::exec(const Op& op) {
         case OP_FUSED_DP: CUDA_CHECK(launch_fused_wgrad_dp(dp_plans_[op.gemm], st)); break;
         case OP_DP_REDUCE: CUDA_CHECK(launch_dp_reduce_sgd(dp_plans_[op.gemm], st)); break;
         case OP_BUMP_EPOCH: CUDA_CHECK(launch_bump_epoch(dp_ctx_->epoch_ptr(), st)); break;
+        case OP_BUMP_STEP: CUDA_CHECK(launch_bump_epoch(gate_step_, st)); break;
         case OP_PP_BUMP: CUDA_CHECK(launch_bump_epoch(pp_ctx_->epoch_ptr(), st)); break;
         case OP_PP_PUSH:
             CUDA_CHECK(launch_pp_push(op.a, op.b, op.n, reinterpret_cast<uint32_t*>(op.c), reinterpret_cast<const uint32_t*>(op.d),
@@ -991,6 +1025,7 @@ static const char* op_name(int kind) {
         case OP_FUSED_DP: return "fused_wgrad_dp";
         case OP_DP_REDUCE: return "dp_reduce_sgd";
         case OP_BUMP_EPOCH: return "bump_epoch";
+        case OP_BUMP_STEP: return "bump_step";
         case OP_PP_BUMP: return "pp_bump_epoch";
         case OP_PP_PUSH: return "pp_push";
         case OP_PP_WAIT: return "pp_wait";

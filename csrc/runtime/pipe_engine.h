@@ -44,7 +44,7 @@ struct LayerSpec {
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
     OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT, OP_NVLS_SGD,
-    OP_PP_PUSH, OP_PP_WAIT, OP_PP_CREDIT, OP_PP_BUMP, OP_WGRAD_GROUP
+    OP_PP_PUSH, OP_PP_WAIT, OP_PP_CREDIT, OP_PP_BUMP, OP_WGRAD_GROUP, OP_BUMP_STEP
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -160,6 +160,9 @@ private:
     std::vector<float*> act_lo_all_, dz_lo_all_; // lo twins (split mode)
     std::vector<std::vector<float*>> act_lo_, dz_lo_;
     float* W_lo_ = nullptr;
+    bool gate_on_ = false;           // grouped wgrad forked next to the chain kernel, gated by device counters
+    uint32_t* gate_ready_ = nullptr; // [L + 1] per-layer counters written by the chain kernel
+    uint32_t* gate_step_ = nullptr;  // steps of THIS engine (bumped in front of the gated kernel)
     bool chain_derive_ = false;      // 3xTF32 chain kernel derives lo twins on chip
     bool w_lo_needed_ = false;       // something reads the W_lo arena (per-layer fwd / dgrad kernels, or the NO_DERIVE chain)
     float* x_lo_sets_[2] = {nullptr, nullptr};

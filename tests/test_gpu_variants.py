@@ -213,3 +213,34 @@ def test_chain_on_chip_lo_twins_inference_engine(monkeypatch):
     eng.synchronize()
     got = eng.probs(0).cpu().double()
     assert float((got - ref).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Gated weight-gradient wave (SSB_WGRAD_GATE=1): the grouped wgrad + SGD kernel runs NEXT TO the chain kernel and
+# starts each layer's tiles when the chain kernel's device counters say dz[l] is final and W_l is no longer read.
+# Same MMAs, same order => bit-identical training; many steps so the monotonic counters, both staging sets and the
+# step counter are exercised, with and without a CUDA graph.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,use_graph,n_mu", [("fp32", True, 4), ("fp32", False, 4), ("tf32", True, 4), ("fp32", True, 8)])
+def test_gated_wgrad_wave_is_bitwise_identical(monkeypatch, precision, use_graph, n_mu):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    steps = 12
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_WGRAD_GROUP", "1")
+    monkeypatch.setenv("SSB_WGRAD_GATE", "0")
+    base = Trainer(SIZES, lr=0.1, precision=precision, use_graph=use_graph, n_mubatches=n_mu)
+    assert "bump_step" not in base.engine.plan_text(0)
+    ref = [base.step(xh[(i % 4) * 128:(i % 4 + 1) * 128], yh[(i % 4) * 128:(i % 4 + 1) * 128]) for i in range(steps)]
+    monkeypatch.setenv("SSB_WGRAD_GATE", "1")
+    tr = Trainer(SIZES, lr=0.1, precision=precision, use_graph=use_graph, n_mubatches=n_mu)
+    assert "bump_step" in tr.engine.plan_text(0)
+    got = [tr.step(xh[(i % 4) * 128:(i % 4 + 1) * 128], yh[(i % 4) * 128:(i % 4 + 1) * 128]) for i in range(steps)]
+    assert got == ref, (got, ref)
+    assert torch.equal(tr.model.arena.weights, base.model.arena.weights)
+    # pipelined API (copy of step i+1 overlaps step i) on top of the gated wave
+    tr2 = Trainer(SIZES, lr=0.1, precision=precision, use_graph=use_graph, n_mubatches=n_mu)
+    lag = [tr2.step_pipelined(xh[(i % 4) * 128:(i % 4 + 1) * 128], yh[(i % 4) * 128:(i % 4 + 1) * 128]) for i in range(steps)] + [tr2.flush()]
+    assert lag[1:] == ref
