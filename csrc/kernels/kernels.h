@@ -158,6 +158,47 @@ cudaError_t launch_fused_wgrad_dp(const FusedDpPlan& plan, cudaStream_t stream);
 cudaError_t launch_dp_reduce_sgd(const FusedDpPlan& plan, cudaStream_t stream);
 cudaError_t launch_bump_epoch(uint32_t* epoch, cudaStream_t stream);
 
+// ---- LL two-shot fused DP path for narrow layers (csrc/kernels/dp_ll.cu): all layers of a stage in ONE launch
+struct DpLLEntry {               // one CTA = one [128 x 32] tile of one layer's weight gradient
+    CUtensorMap tmA, tmB, tmAlo, tmBlo;   // dZ (MN-major A), X (MN-major B) and their lo twins
+    int m0, n0;                  // tile origin in (out, in)
+    int m_total, n_total, k_total;
+    int split, has_bias;
+    int tile;                    // index in the landing zones
+    int64_t w_offset;            // float offset of the layer's [out, ld] block in the arena
+    int ldw;
+    const uint32_t* gate_flag;   // chain-kernel counter this tile waits for (nullptr: ordered by the stream instead)
+    uint32_t gate_mult;
+};
+struct DpLLParams {
+    int dp, rank;
+    float lr;
+    const uint32_t* epoch_ptr;   // DP step counter (same value on every replica)
+    const uint32_t* gate_step;   // steps of the launching engine (gate target = gate_mult * *gate_step)
+    int n_tiles, stages;
+    float* W;                    // local weight arena
+    uint4* llA[kMaxDp];          // reduce-scatter landing zones  [parity][src][tile][128 / dp rows][17 lines]
+    uint4* llC[kMaxDp];          // all-gather landing zones      [parity][tile][128 rows][17 lines]
+};
+struct DpLLLayer {
+    const float *dZ, *X, *dZ_lo, *X_lo;
+    int lddz, ldx, in, out, ldw;
+    int64_t w_offset;
+    const uint32_t* gate_flag;
+    uint32_t gate_mult;
+};
+struct DpLLPlan {
+    DpLLParams p;
+    DpLLEntry* entries_dev;
+    int grid, smem_bytes;
+};
+int dp_ll_tiles(int in, int out);
+size_t dp_ll_zone_lines(int dp, int n_tiles);
+const char* dp_ll_plan(DpLLPlan* plan, const DpLLLayer* layers, int n_layers, int rows, const DpLLParams& base);
+void dp_ll_free(DpLLPlan* plan);
+cudaError_t dp_ll_configure();
+cudaError_t launch_dp_ll(const DpLLPlan& plan, cudaStream_t stream);
+
 // ---- layer-chain kernel (csrc/kernels/mlp_chain.cu) --------------------------------------
 static constexpr int kChainMaxLayers = 16;
 struct ChainLayer {

@@ -51,6 +51,19 @@ DpContext::DpContext(int dp, int rank, int64_t arena_numel, const std::vector<st
     alloc((void**)&arrive_, (size_t)dp_ * slots_per_src_ * 4);
     alloc((void**)&done_, (size_t)tiles_total_ * 4);
     alloc((void**)&epoch_, 64);
+    // LL landing zones: only for stages whose [128 x 32] tiles all fit on the chip next to the chain kernel
+    {
+        int tiles = 0;
+        for (const auto& g : geom_) tiles += dp_ll_tiles(g.in, g.out);
+        const bool ok = tiles > 0 && tiles <= 128 && dp_ >= 2 && (128 % dp_) == 0 && !(getenv("SSB_DP_LL") && atoi(getenv("SSB_DP_LL")) == 0);
+        if (ok) {
+            ll_tiles_ = tiles;
+            const size_t bytes = dp_ll_zone_lines(dp_, tiles) * sizeof(uint4);
+            alloc((void**)&llA_, bytes);
+            alloc((void**)&llC_, bytes);
+            llA_peers_[rank_] = llA_; llC_peers_[rank_] = llC_;
+        }
+    }
     for (int r = 0; r < kMaxDp; ++r) { peers_.W[r] = nullptr; peers_.stage[r] = nullptr; peers_.arrive[r] = nullptr; peers_.done[r] = nullptr; }
     peers_.W[rank_] = W_; peers_.stage[rank_] = stage_; peers_.arrive[rank_] = arrive_; peers_.done[rank_] = done_;
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -60,14 +73,21 @@ DpContext::~DpContext() {
     cudaDeviceSynchronize();
     for (void* p : opened_) cudaIpcCloseMemHandle(p);
     cudaFree(W_); cudaFree(stage_); cudaFree(arrive_); cudaFree(done_); cudaFree(epoch_);
+    if (llA_) cudaFree(llA_);
+    if (llC_) cudaFree(llC_);
 }
 
 std::string DpContext::export_handles() const {
-    cudaIpcMemHandle_t h[4];
+    cudaIpcMemHandle_t h[6];
+    memset(h, 0, sizeof(h));
     CUDA_CHECK(cudaIpcGetMemHandle(&h[0], W_));
     CUDA_CHECK(cudaIpcGetMemHandle(&h[1], stage_));
     CUDA_CHECK(cudaIpcGetMemHandle(&h[2], arrive_));
     CUDA_CHECK(cudaIpcGetMemHandle(&h[3], done_));
+    if (ll_tiles_ > 0) {
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[4], llA_));
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[5], llC_));
+    }
     return std::string(reinterpret_cast<const char*>(h), sizeof(h));
 }
 
@@ -75,17 +95,29 @@ void DpContext::open_peers(const std::vector<std::string>& handles) {
     if ((int)handles.size() != dp_) throw std::runtime_error("DpContext::open_peers: need one handle blob per DP rank");
     for (int r = 0; r < dp_; ++r) {
         if (r == rank_) continue;
-        if (handles[r].size() != 4 * sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("DpContext: bad handle blob");
-        cudaIpcMemHandle_t h[4];
+        if (handles[r].size() != 6 * sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("DpContext: bad handle blob");
+        cudaIpcMemHandle_t h[6];
         memcpy(h, handles[r].data(), sizeof(h));
-        void* ptr[4];
-        for (int i = 0; i < 4; ++i) {
+        void* ptr[6] = {};
+        const int n = ll_tiles_ > 0 ? 6 : 4;
+        for (int i = 0; i < n; ++i) {
             CUDA_CHECK(cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess));
             opened_.push_back(ptr[i]);
         }
         peers_.W[r] = (float*)ptr[0]; peers_.stage[r] = (float*)ptr[1];
         peers_.arrive[r] = (uint32_t*)ptr[2]; peers_.done[r] = (uint32_t*)ptr[3];
+        llA_peers_[r] = (uint4*)ptr[4]; llC_peers_[r] = (uint4*)ptr[5];
     }
+}
+
+DpLLParams DpContext::ll_params() const {
+    DpLLParams p{};
+    p.dp = dp_; p.rank = rank_; p.lr = lr_;
+    p.epoch_ptr = epoch_; p.gate_step = nullptr;
+    p.n_tiles = ll_tiles_; p.stages = 2;
+    p.W = W_;
+    for (int r = 0; r < kMaxDp; ++r) { p.llA[r] = llA_peers_[r]; p.llC[r] = llC_peers_[r]; }
+    return p;
 }
 
 DpLayerParams DpContext::layer_params(int i) const {

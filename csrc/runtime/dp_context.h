@@ -46,6 +46,10 @@ public:
     int64_t stage_bytes() const { return (int64_t)dp_ * stage_src_stride_ * 4; }
     const std::vector<DpLayerGeom>& geometry() const { return geom_; }
     int total_ctas() const { return total_ctas_; }   // sum of tiles over layers: all co-resident if <= #SMs
+    // LL two-shot path (dp_ll.cu): landing zones exist when every layer is narrow enough for all tiles to be co-resident
+    bool ll_enabled() const { return ll_tiles_ > 0; }
+    int ll_tiles() const { return ll_tiles_; }
+    DpLLParams ll_params() const;
 
 private:
     int dp_, rank_;
@@ -58,6 +62,9 @@ private:
     float *W_ = nullptr, *stage_ = nullptr;
     uint32_t *arrive_ = nullptr, *done_ = nullptr, *epoch_ = nullptr;
     DpPeers peers_{};
+    int ll_tiles_ = 0;
+    uint4 *llA_ = nullptr, *llC_ = nullptr;
+    uint4 *llA_peers_[kMaxDp] = {}, *llC_peers_[kMaxDp] = {};
     std::vector<void*> opened_;
 };
 

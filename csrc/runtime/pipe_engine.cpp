@@ -68,6 +68,7 @@ PipeEngine::~PipeEngine() {
     for (auto s : streams_) cudaStreamDestroy(s);
     for (auto& cp : chain_plans_) chain_plan_free(&cp);
     for (auto& gp : group_plans_) gemm_group_free(&gp);
+    for (auto& lp : ll_plans_) dp_ll_free(&lp);
     for (auto p : owned_) cudaFree(p);
     if (loss_host_) cudaFreeHost(loss_host_);
 }
@@ -728,8 +729,11 @@ void PipeEngine::build_coalesced() {
     // the dgrad that reads W_l retired - W_l is updated in place) before their first TMA load.  Only the last layers'
     // tiles remain behind the chain kernel; the launch gap and the rest of the wave hide behind the backward pass.
     const bool group_env = getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
-    gate_on_ = chain && cfg_.training && cfg_.dp_mode == 0 && group_env && getenv("SSB_WGRAD_GATE") != nullptr &&
-               atoi(getenv("SSB_WGRAD_GATE")) > 0;
+    auto env_on = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) > 0 : dflt; };
+    // fused DP over narrow layers: the LL two-shot kernel (dp_ll.cu), all layers in one launch, gated the same way
+    const bool ll_on = chain && cfg_.training && cfg_.dp_mode == 2 && dp_ctx_ != nullptr && dp_ctx_->ll_enabled();
+    gate_on_ = chain && cfg_.training &&
+               ((cfg_.dp_mode == 0 && group_env && env_on("SSB_WGRAD_GATE", false)) || (ll_on && env_on("SSB_DP_GATE", true)));
     if (gate_on_ && gate_ready_ == nullptr) {
         uint32_t* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, 256));
@@ -784,6 +788,7 @@ void PipeEngine::build_coalesced() {
     // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
     const bool group_wgrad = (fuse || cfg_.dp_mode == 3) && chain && group_env;
     std::vector<GemmPlan> grouped;
+    std::vector<DpLLLayer> ll_layers;
     int ev_bump = -1;
     if (fused_dp) {
         if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
@@ -805,6 +810,15 @@ void PipeEngine::build_coalesced() {
                                   mask, act_ld_[l - 1], lo_dgrad(l, -1)));
             add_gemm(g, 0, l);
             ev_dg = emit_record(0);
+        }
+        if (fused_dp && ll_on) {
+            DpLLLayer ly{};
+            ly.dZ = dz_all_[l]; ly.X = act_all_[l - 1];
+            ly.dZ_lo = cfg_.split ? dz_lo_all_[l] : nullptr; ly.X_lo = cfg_.split ? act_lo_all_[l - 1] : nullptr;
+            ly.lddz = act_ld_[l]; ly.ldx = act_ld_[l - 1]; ly.in = ls.in; ly.out = ls.out; ly.ldw = ls.ld; ly.w_offset = ls.offset;
+            if (gate_on_) { ly.gate_flag = gate_ready_ + (l >= 2 ? l - 1 : 1); ly.gate_mult = 8u * (uint32_t)M; }
+            ll_layers.push_back(ly);
+            continue;
         }
         if (fused_dp) {
             // ONE kernel per layer: wgrad GEMM -> NVLink push -> owner reduce -> SGD -> weight broadcast.
@@ -861,6 +875,24 @@ void PipeEngine::build_coalesced() {
             ops_.push_back(ar);
         }
     }
+    if (!ll_layers.empty()) {
+        // deepest layer first: its tiles get the lowest block indices, i.e. they are resident first and their gate opens first
+        DpLLParams base = dp_ctx_->ll_params();
+        base.gate_step = gate_on_ ? gate_step_ : nullptr;
+        DpLLPlan lp;
+        check(dp_ll_plan(&lp, ll_layers.data(), (int)ll_layers.size(), rows, base));
+        ll_plans_.push_back(lp);
+        if (gate_on_) {
+            Op bs;
+            bs.kind = OP_BUMP_STEP; bs.stream = s_dp_;
+            ops_.push_back(bs);
+        } else {
+            emit_wait(s_dp_, emit_record(0));               // behind the chain kernel
+        }
+        Op lo;
+        lo.kind = OP_DP_LL; lo.stream = s_dp_; lo.gemm = (int)ll_plans_.size() - 1;
+        ops_.push_back(lo);
+    }
     if (group_wgrad && !grouped.empty()) {
         GemmGroupPlan gp;
         check(gemm_group_plan(&gp, grouped.data(), (int)grouped.size()));
@@ -911,7 +943,7 @@ void PipeEngine::finish_build() {
             op.kind == OP_SGD || op.kind == OP_ARGMAX || op.kind == OP_FUSED_DP || op.kind == OP_DP_REDUCE ||
             op.kind == OP_BUMP_EPOCH || op.kind == OP_CHAIN || op.kind == OP_SPLIT || op.kind == OP_NVLS_SGD ||
             op.kind == OP_PP_PUSH || op.kind == OP_PP_WAIT || op.kind == OP_PP_CREDIT || op.kind == OP_PP_BUMP ||
-            op.kind == OP_WGRAD_GROUP || op.kind == OP_BUMP_STEP)
+            op.kind == OP_WGRAD_GROUP || op.kind == OP_BUMP_STEP || op.kind == OP_DP_LL)
             ++kernels_per_step_;
     }
     built_ = true;
@@ -926,6 +958,7 @@ void PipeEngine::finish_build() {
     if (cfg_.split && cfg_.is_first) ++kernels_per_step_;   // + the staged-input split issued on the copy stream every step
     if (!chain_plans_.empty()) CUDA_CHECK(chain_configure());
     if (cfg_.dp_mode == 2) CUDA_CHECK(fused_dp_configure());
+    if (!ll_plans_.empty()) CUDA_CHECK(dp_ll_configure());
     comm_timing_ = getenv("SSB_COMM_TIMING") != nullptr;   // needs timing events between ops: eager plan walk
     if (cfg_.use_graph && !comm_timing_) {
         for (int set = 0; set < 2; ++set) {
@@ -995,6 +1028,7 @@ void PipeEngine::exec(const Op& op) {
         case OP_DP_REDUCE: CUDA_CHECK(launch_dp_reduce_sgd(dp_plans_[op.gemm], st)); break;
         case OP_BUMP_EPOCH: CUDA_CHECK(launch_bump_epoch(dp_ctx_->epoch_ptr(), st)); break;
         case OP_BUMP_STEP: CUDA_CHECK(launch_bump_epoch(gate_step_, st)); break;
+        case OP_DP_LL: CUDA_CHECK(launch_dp_ll(ll_plans_[op.gemm], st)); break;
         case OP_PP_BUMP: CUDA_CHECK(launch_bump_epoch(pp_ctx_->epoch_ptr(), st)); break;
         case OP_PP_PUSH:
             CUDA_CHECK(launch_pp_push(op.a, op.b, op.n, reinterpret_cast<uint32_t*>(op.c), reinterpret_cast<const uint32_t*>(op.d),
@@ -1026,6 +1060,7 @@ static const char* op_name(int kind) {
         case OP_DP_REDUCE: return "dp_reduce_sgd";
         case OP_BUMP_EPOCH: return "bump_epoch";
         case OP_BUMP_STEP: return "bump_step";
+        case OP_DP_LL: return "dp_ll";
         case OP_PP_BUMP: return "pp_bump_epoch";
         case OP_PP_PUSH: return "pp_push";
         case OP_PP_WAIT: return "pp_wait";

@@ -44,7 +44,7 @@ struct LayerSpec {
 enum OpKind : int {
     OP_GEMM = 0, OP_LOSS_HEAD, OP_SOFTMAX, OP_RELU_MASK, OP_SGD, OP_COMM_GROUP, OP_ALLREDUCE, OP_FUSED_DP,
     OP_WAIT, OP_RECORD, OP_MEMCPY_LOSS, OP_ARGMAX, OP_DP_REDUCE, OP_BUMP_EPOCH, OP_CHAIN, OP_SPLIT, OP_NVLS_SGD,
-    OP_PP_PUSH, OP_PP_WAIT, OP_PP_CREDIT, OP_PP_BUMP, OP_WGRAD_GROUP, OP_BUMP_STEP
+    OP_PP_PUSH, OP_PP_WAIT, OP_PP_CREDIT, OP_PP_BUMP, OP_WGRAD_GROUP, OP_BUMP_STEP, OP_DP_LL
 };
 
 struct CommItem {   // one send or recv inside a group
@@ -186,6 +186,7 @@ private:
     std::vector<FusedDpPlan> dp_plans_;
     std::vector<ChainPlan> chain_plans_;
     std::vector<GemmGroupPlan> group_plans_;
+    std::vector<DpLLPlan> ll_plans_;
     bool chain_ok_ = false;
     unsigned long long* chain_dbg_ = nullptr;
     int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd);

@@ -273,3 +273,25 @@ def test_train_eval_alternation_on_one_pipeline_comm(pp, sched, tmp_path):
     for p0, a, b in zip(init, params, [p.data for p in model.parameters()]):
         upd_err = float(((a - p0) - (b - p0)).norm() / ((b - p0).norm() + 1e-12))
         assert upd_err < 3e-2, upd_err
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LL two-shot fused DP kernel (csrc/kernels/dp_ll.cu; default for narrow layers) against the flag-protocol kernels it
+# replaces (SSB_DP_LL=0): same MMAs, same fixed-rank-order sum, same update expression => bit-identical weights.
+# Also with the gate off (SSB_DP_GATE=0: the kernel is ordered behind the chain kernel by a graph edge).
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dp", [2, 4, 8])
+def test_dp_ll_kernel_is_bitwise_identical_to_flag_protocol(dp, tmp_path):
+    if torch.cuda.device_count() < dp:
+        pytest.skip(f"needs {dp} GPUs")
+    outs = {}
+    for name, env in (("flags", {"SSB_DP_LL": "0"}), ("ll_gated", {"SSB_DP_LL": "1", "SSB_DP_GATE": "1"}),
+                      ("ll_edge", {"SSB_DP_LL": "1", "SSB_DP_GATE": "0"})):
+        d = tmp_path / name
+        d.mkdir()
+        _run(dp, 1, "naive", "fused", d, extra_env=env)          # also checks the oracle tolerance and replica equality
+        outs[name] = torch.load(d / "stage0.pt")
+    for name in ("ll_gated", "ll_edge"):
+        assert outs[name]["losses"] == outs["flags"]["losses"], name
+        for a, b in zip(outs[name]["params"], outs["flags"]["params"]):
+            assert torch.equal(a, b), name
