@@ -51,11 +51,6 @@ struct GemmParams {
     int k_splits;                 // 0 / 1 = off
     float* partial;
     unsigned int* tile_counter;   // zero before the first launch; re-armed by the kernel
-    // WGRAD launched CONCURRENTLY with the kernel that produces its operands (the layer-chain kernel): the TMA producer
-    // first waits until *gate_flag >= gate_mult * *gate_step (device counters; release/acquire at gpu scope).
-    const uint32_t* gate_flag;    // nullptr = not gated
-    const uint32_t* gate_step;
-    uint32_t gate_mult;
 };
 
 struct GemmPlan {          // a fully prepared launch (tensor maps are 128 B each)
@@ -227,7 +222,6 @@ struct ChainParams {
     int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
-    int derive;                      // split mode: lo twins of the streamed tiles are derived on chip (no W_lo / X_lo loads)
     uint32_t* ready;                 // optional [n_layers + 1] device counters: every epilogue warp of every CTA adds 1 to
                                      // ready[l] once its part of dz[l] (and everything it wrote before) is globally visible
     unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only
@@ -238,9 +232,8 @@ struct ChainPlan {
     int grid, smem_bytes;
 };
 bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out_dim, bool has_loss, bool split = false);
-// split_mode: 0 = single-pass TF32; 1 = 3xTF32 with lo twins LOADED from W_lo / x_lo; 2 = 3xTF32 with lo twins DERIVED on chip
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       int split_mode = 0, const float* W_lo = nullptr, const float* x_lo = nullptr);
+                       const float* W_lo = nullptr, const float* x_lo = nullptr);
 bool chain_budget(int mb_rows, bool split, int* kps, int* stages, int* smem_bytes);   // host arithmetic only
 void chain_plan_free(ChainPlan* plan);
 cudaError_t chain_configure();

@@ -24,8 +24,6 @@
 namespace ssb {
 
 static constexpr int kThreads = 320;                      // 2 control warps + 8 epilogue warps
-static constexpr int kSplitWarps = 2;                     // DERIVE: warps 10..11 derive the lo twins of the streamed tiles
-static constexpr int kThreadsDerive = kThreads + 32 * kSplitWarps;
 static constexpr uint32_t kBlockM = 128;
 static constexpr uint32_t kBlockK = 32;
 static constexpr uint32_t kABytes = kBlockM * 128;
@@ -58,18 +56,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define DBG(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = gtime(); } while (0)
 
 // SPLIT (3xTF32) is a compile-time switch: the single-pass TF32 instantiation carries none of the lo-twin code.
-//
-// DERIVE (SPLIT only, the default fp32 path): the kernel is bound by how fast ONE SM can pull operand bytes out of L2
-// (measured: 55 GB/s per SM through TMA, independent of ring depth and of cluster multicast - profiles/microbench.md),
-// and every micro-batch CTA streams all weights of the stage.  Loading the lo twins W - trunc_tf32(W) doubled those
-// bytes.  In this variant the TMA fetches only the raw fp32 tiles; two extra warps derive the lo twin of every ring
-// slot in shared memory (elementwise, so the swizzled layout carries over unchanged), fence it to the async proxy and
-// hand the slot to the MMA warp through a second per-slot mbarrier.  The derivation runs ahead of the math like the
-// loads do (weights do not depend on activations) and moves 123 GB/s per SM, so the ring stays ingest-bound at HALF
-// the bytes; the W_lo arena, its refresh kernel after every optimizer step and the X_lo loads disappear.
-template <bool SPLIT, bool DERIVE = false>
-__global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_chain_kernel(const ChainParams p) {
-    static_assert(SPLIT || !DERIVE, "DERIVE is a variant of the 3xTF32 kernel");
+// (Round 2 also tried deriving the lo twins of the streamed weight tiles in shared memory instead of loading them - half
+// the L2->SM bytes, bit-identical results - but with only 3 ring slots of 40 KB the extra split stage in the slot cycle
+// cost more than the bytes saved: 92.8 vs 78.7 us/step.  Removed; see profiles/variants_r2.md.)
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t smem_base = (raw + 1023u) & ~1023u;
@@ -90,22 +81,20 @@ __global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_cha
     const uint32_t bar_base = abuf0 + n_abuf * abuf_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-    auto split_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };   // DERIVE: lo twin of slot s is ready
-    const uint32_t tmem_full_bar = bar_base + 8u * (3 * p.stages);
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
     const uint32_t act_ready_bar = tmem_full_bar + 8u;
     const uint32_t tmem_slot = act_ready_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (3 * p.stages + 2));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)N) tmem_cols <<= 1;
     // loss-head transpose scratch [N][kScratchLd] floats, behind the barriers (128 B further)
-    const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (3 * p.stages + 2) + 128u;
+    const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
-            mbar_init(split_bar(s), kSplitWarps);            // one arrive per splitter warp (DERIVE)
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(act_ready_bar, 8);                         // one arrive per epilogue warp
@@ -145,12 +134,12 @@ __global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_cha
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * ((SPLIT && !DERIVE) ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * (kABytes + (with_x ? b_bytes : 0u)) * (SPLIT ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
                                 tma_load_2d(a_dst + j * kABytes, p.maps + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                 if (with_x)
                                     tma_load_2d(a_dst + stage_b_off + j * b_bytes, p.maps + 2 * L, full_bar(s), (kb0 + j) * kBlockK, row0);
-                                if (SPLIT && !DERIVE) {
+                                if (SPLIT) {
                                     tma_load_2d(a_dst + half_stage + j * kABytes, p.maps + lo_base + 2 * (l - 1), full_bar(s), (kb0 + j) * kBlockK, 0);
                                     if (with_x)
                                         tma_load_2d(a_dst + half_stage + stage_b_off + j * b_bytes, p.maps + lo_base + 2 * L, full_bar(s),
@@ -171,13 +160,13 @@ __global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_cha
                         const uint32_t a_dst = smem_base + s * stage_bytes;
                         if (elect_one()) {
                             DBG(0, it);
-                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * ((SPLIT && !DERIVE) ? 2u : 1u));
+                            mbar_arrive_expect_tx(full_bar(s), (uint32_t)cnt * kABytes * (SPLIT ? 2u : 1u));
                             for (int j = 0; j < cnt; ++j) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     tma_load_2d(a_dst + j * kABytes + i * kPanelBytes, p.maps + 2 * (l - 1) + 1, full_bar(s), 32 * i,
                                                 (kb0 + j) * kBlockK);
-                                    if (SPLIT && !DERIVE)
+                                    if (SPLIT)
                                         tma_load_2d(a_dst + half_stage + j * kABytes + i * kPanelBytes, p.maps + lo_base + 2 * (l - 1) + 1,
                                                     full_bar(s), 32 * i, (kb0 + j) * kBlockK);
                                 }
@@ -206,7 +195,6 @@ __global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_cha
                     const int cnt = min(p.kps, nkb - kb0);
                     const int s = it % p.stages;
                     mbar_wait(full_bar(s), (it / p.stages) & 1);
-                    if constexpr (DERIVE) mbar_wait(split_bar(s), (it / p.stages) & 1);   // lo twin derived + fenced
                     tc_fence_after();
                     if (kb0 + cnt >= nkb && lane == 0) DBG(1, 3 * gemm_i + 1);
                     const uint32_t a_src = smem_base + s * stage_bytes;
@@ -260,56 +248,6 @@ __global__ void __launch_bounds__(DERIVE ? kThreadsDerive : kThreads, 1) mlp_cha
                 }
             }
         }
-    } else if (DERIVE && warp >= kThreads / 32) {
-        // ============================================================ lo-twin splitters (DERIVE)
-        // Same slot sequence as the producer.  Per slot: wait for the TMA bytes, lo = x - trunc_tf32(x) for the `cnt`
-        // weight tiles (and the X tiles of layer 1) into the slot's second half at the same offsets, make the generic-
-        // proxy writes visible to the async proxy (tcgen05.mma reads operands through it), arrive on split_bar.
-        // The slot cannot be rewritten under us: the producer re-arms it only after the MMAs that read it retired.
-        const int st = (int)threadIdx.x - kThreads;              // 0 .. 127
-        constexpr int kSplitThreads = 32 * kSplitWarps;
-        int it = 0;
-        auto derive = [&](int cnt, bool with_x) {
-            const int s = it % p.stages;
-            mbar_wait(full_bar(s), (it / p.stages) & 1);
-            uint8_t* base = smem_gen + (size_t)s * stage_bytes;
-            // all loads of a batch first, then the math and the stores: a load -> lo -> store chain per element costs a
-            // full shared-memory round trip each (measured: 120 cycles per float4, the ring ran at 16 GB/s)
-            constexpr int kU = 8;
-            auto split_region = [&](uint32_t off, int n_vec) {
-                for (int v0 = st; v0 < n_vec; v0 += kSplitThreads * kU) {
-                    float4 x[kU];
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int v = v0 + u * kSplitThreads;
-                        if (v < n_vec) x[u] = *reinterpret_cast<const float4*>(base + off + 16 * v);
-                    }
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int v = v0 + u * kSplitThreads;
-                        if (v < n_vec)
-                            *reinterpret_cast<float4*>(base + half_stage + off + 16 * v) =
-                                make_float4(tf32_lo(x[u].x), tf32_lo(x[u].y), tf32_lo(x[u].z), tf32_lo(x[u].w));
-                    }
-                }
-            };
-            split_region(0u, cnt * (int)(kABytes / 16));
-            if (with_x) split_region(stage_b_off, cnt * (int)(b_bytes / 16));
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(split_bar(s));
-            ++it;
-        };
-        if (p.do_fwd)
-            for (int l = 1; l <= L; ++l) {
-                const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
-                for (int kb0 = 0; kb0 < nkb; kb0 += p.kps) derive(min(p.kps, nkb - kb0), l == 1);
-            }
-        if (p.do_bwd)
-            for (int l = L; l >= bwd_lo; --l) {
-                const int nkb = (p.layers[l - 1].out + (int)kBlockK - 1) / (int)kBlockK;
-                for (int kb0 = 0; kb0 < nkb; kb0 += p.kps) derive(min(p.kps, nkb - kb0), false);
-            }
     } else {
         // ============================================================ epilogue warps
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
@@ -597,7 +535,7 @@ bool chain_budget(int mb_rows, bool split, int* kps_out, int* stages_out, int* s
     if (stages > 8) stages = 8;
     *kps_out = kps;
     *stages_out = stages;
-    *smem_bytes_out = stages * stage_bytes + (split ? 4 : 2) * abuf_bytes + 1024 + 8 * (3 * stages + 3) + 16 + scratch_bytes;
+    *smem_bytes_out = stages * stage_bytes + (split ? 4 : 2) * abuf_bytes + 1024 + 8 * (2 * stages + 3) + 16 + scratch_bytes;
     return true;
 }
 
@@ -618,17 +556,15 @@ bool chain_eligible(const ChainLayer* layers, int n_layers, int mb_rows, int out
 }
 
 const char* chain_plan(ChainPlan* plan, const ChainParams& params, const float* x, int ldx, int total_rows, int n_mubatches,
-                       int split_mode, const float* W_lo, const float* x_lo) {
+                       const float* W_lo, const float* x_lo) {
     *plan = ChainPlan{};
     ChainParams& p = plan->p;
     p = params;
     const int L = p.n_layers;
     p.n_pad = (p.mb_rows + 15) / 16 * 16;
-    p.split = split_mode != 0 ? 1 : 0;
-    p.derive = split_mode == 2 ? 1 : 0;
-    if (split_mode == 1 && W_lo == nullptr) return "chain_plan: split_mode 1 needs the W_lo arena";
+    p.split = (W_lo != nullptr) ? 1 : 0;
     const int nmaps = 2 * L + 1;
-    const int halves = (split_mode == 1) ? 2 : 1;            // derive mode loads no twins: no maps for them
+    const int halves = p.split ? 2 : 1;
     std::vector<CUtensorMap> host(nmaps * halves);
     for (int half = 0; half < halves; ++half) {
         const float* Wb = half ? W_lo : p.W;
@@ -667,13 +603,11 @@ void chain_plan_free(ChainPlan* plan) {
 cudaError_t chain_configure() {
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
-    if (plan.p.split && plan.p.derive) mlp_chain_kernel<true, true><<<plan.grid, kThreadsDerive, plan.smem_bytes, stream>>>(plan.p);
-    else if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     else mlp_chain_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
     return cudaGetLastError();
 }

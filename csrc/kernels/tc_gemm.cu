@@ -102,13 +102,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         // converged warp; one elect.sync-chosen lane issues (no ELECT/BRA.U.ANY uniformization loops)
-        if (MODE == GEMM_WGRAD && p.gate_flag != nullptr) {
-            // gated launch: this kernel runs next to the chain kernel that produces dZ / activations; wait for the
-            // producer's per-layer counter, then order its generic-proxy stores before my async-proxy (TMA) reads
-            wait_counter_ge_gpu(p.gate_flag, p.gate_mult * ld_acquire_gpu(p.gate_step));
-            fence_proxy_async_global();
-            __syncwarp();
-        }
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % p.stages;
             const uint32_t ph = (kb / p.stages) & 1;

@@ -271,11 +271,8 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
         cp.dbg = chain_dbg_;
     }
     ChainPlan plan;
-    // 3xTF32: the lo twins of the streamed weight / input tiles are derived on chip (chain_derive_), or loaded from the
-    // W_lo arena and the staged X_lo (SSB_CHAIN_NO_DERIVE=1: the round-1 path, kept for A/B measurements)
-    const int split_mode = !cfg_.split ? 0 : (chain_derive_ ? 2 : 1);
-    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, split_mode,
-                                 split_mode == 1 ? W_lo_ : nullptr, split_mode == 1 ? act_lo_all_[0] : nullptr);
+    const char* err = chain_plan(&plan, cp, act_all_[0], act_ld_[0], cfg_.n_mu * cfg_.mb_rows, n_mu, cfg_.split ? W_lo_ : nullptr,
+                                 cfg_.split ? act_lo_all_[0] : nullptr);
     if (err) throw std::runtime_error(std::string("PipeEngine chain plan: ") + err);
     chain_plans_.push_back(plan);
     Op op;
@@ -324,10 +321,7 @@ void PipeEngine::build(const std::vector<std::tuple<int, int, int>>& instrs) {
         for (int l = 0; l < nl; ++l) { cl[l].in = cfg_.layers[l].in; cl[l].out = cfg_.layers[l].out; }
         chain_ok_ = L_ >= 1 && L_ <= kChainMaxLayers && !getenv("SSB_NO_CHAIN") &&
                     chain_eligible(cl, L_, cfg_.mb_rows, cfg_.out_dim, cfg_.is_last != 0, cfg_.split != 0);
-        // With the chain kernel deriving lo twins on chip nothing reads the W_lo arena any more (the weight-gradient
-        // GEMMs read the lo twins of activations and gradients only): no refresh kernel after the optimizer step.
-        chain_derive_ = chain_ok_ && cfg_.split && !(getenv("SSB_CHAIN_NO_DERIVE") && atoi(getenv("SSB_CHAIN_NO_DERIVE")) > 0);
-        w_lo_needed_ = cfg_.split && !chain_derive_;
+        w_lo_needed_ = cfg_.split != 0;      // chain kernel and per-layer fwd / dgrad kernels load the weights' lo twins
     }
     if (pp_ctx_) {
         // peer-memory transport: the neighbours write straight into my receive slots, which therefore live in the
@@ -723,17 +717,16 @@ void PipeEngine::build_coalesced() {
         ops_.push_back(sp);
     }
     const bool chain = chain_ok_;
-    // Gated weight-gradient wave (SSB_WGRAD_GATE, with the grouped launch): the grouped wgrad + SGD kernel is forked at
-    // the START of the step next to the chain kernel instead of behind it.  The chain kernel's epilogue warps count up a
-    // per-layer device counter when dz[l] is globally visible; the CTAs of layer l wait for ready[l-1] (dz[l] final AND
-    // the dgrad that reads W_l retired - W_l is updated in place) before their first TMA load.  Only the last layers'
-    // tiles remain behind the chain kernel; the launch gap and the rest of the wave hide behind the backward pass.
+    // Gated launch: the LL data-parallel kernel (dp_ll.cu) is forked at the START of the step next to the chain kernel
+    // instead of behind it.  The chain kernel's epilogue warps count up a per-layer device counter when dz[l] is
+    // globally visible; the tiles of layer l wait for ready[l-1] (dz[l] final AND the dgrad that reads W_l retired -
+    // W_l is updated in place) before their first TMA load.  Only the last layers' tiles remain behind the chain kernel.
+    // (The same gate in front of the single-GPU grouped wgrad launch was measured neutral - 79.7 vs 78.7 us - and removed.)
     const bool group_env = getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
     auto env_on = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) > 0 : dflt; };
     // fused DP over narrow layers: the LL two-shot kernel (dp_ll.cu), all layers in one launch, gated the same way
     const bool ll_on = chain && cfg_.training && cfg_.dp_mode == 2 && dp_ctx_ != nullptr && dp_ctx_->ll_enabled();
-    gate_on_ = chain && cfg_.training &&
-               ((cfg_.dp_mode == 0 && group_env && env_on("SSB_WGRAD_GATE", false)) || (ll_on && env_on("SSB_DP_GATE", true)));
+    gate_on_ = ll_on && env_on("SSB_DP_GATE", true);
     if (gate_on_ && gate_ready_ == nullptr) {
         uint32_t* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, 256));
@@ -857,11 +850,6 @@ void PipeEngine::build_coalesced() {
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
         if (group_wgrad) {                                  // launched together after the loop
-            if (gate_on_) {
-                g.p.gate_flag = gate_ready_ + (l >= 2 ? l - 1 : 1);
-                g.p.gate_step = gate_step_;
-                g.p.gate_mult = 8u * (uint32_t)M;          // 8 epilogue warps per chain CTA, one CTA per micro-batch
-            }
             grouped.push_back(g);
             continue;
         }
@@ -899,14 +887,6 @@ void PipeEngine::build_coalesced() {
         group_plans_.push_back(gp);
         Op go;
         go.kind = OP_WGRAD_GROUP; go.stream = 0; go.gemm = (int)group_plans_.size() - 1;
-        if (gate_on_) {                                     // own branch, forked at the begin of the step
-            const int gs = sw(0);
-            use(gs);
-            Op bs;
-            bs.kind = OP_BUMP_STEP; bs.stream = gs;
-            ops_.push_back(bs);
-            go.stream = gs;
-        }
         ops_.push_back(go);
     }
     if (!fuse && !fused_dp) {

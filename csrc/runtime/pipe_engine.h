@@ -163,8 +163,7 @@ private:
     bool gate_on_ = false;           // grouped wgrad forked next to the chain kernel, gated by device counters
     uint32_t* gate_ready_ = nullptr; // [L + 1] per-layer counters written by the chain kernel
     uint32_t* gate_step_ = nullptr;  // steps of THIS engine (bumped in front of the gated kernel)
-    bool chain_derive_ = false;      // 3xTF32 chain kernel derives lo twins on chip
-    bool w_lo_needed_ = false;       // something reads the W_lo arena (per-layer fwd / dgrad kernels, or the NO_DERIVE chain)
+    bool w_lo_needed_ = false;       // 3xTF32: the chain kernel and the per-layer fwd / dgrad kernels load the weights' lo twins
     float* x_lo_sets_[2] = {nullptr, nullptr};
     GemmLo lo_fwd(int l, int mu) const;
     GemmLo lo_dgrad(int l, int mu) const;
