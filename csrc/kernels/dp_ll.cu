@@ -59,6 +59,7 @@ __device__ __forceinline__ uint4 wait_ll(const uint4* p, uint4 v, uint32_t epoch
     return v;
 }
 
+template <int DP>
 __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntry* __restrict__ entries, const DpLLParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
         const int m_local = q * 32 + lane;                       // row of the tile = TMEM lane
         const int etid = (warp - 2) * 32 + lane;                 // 0..127
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int rpo = (int)kBlockM / p.dp;                     // rows per owner
+        constexpr int rpo = (int)kBlockM / DP;                   // rows per owner
         const int lpr = e.has_bias ? 17 : 16;                    // lines per row (line 16 = bias gradient / new bias)
         const int rows_valid = min((int)kBlockM, e.m_total - e.m0);
         float* own = reinterpret_cast<float*>(smem_gen + own_off);
@@ -209,55 +210,77 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
                 const int row = idx / lpr, j = idx - row * lpr;
                 const int owner = row / rpo;
                 if (owner == p.rank) continue;
-                uint4* dst = p.llA[owner] + ((((size_t)parity * p.dp + p.rank) * p.n_tiles + e.tile) * rpo + (row - owner * rpo)) * 17 + j;
+                uint4* dst = p.llA[owner] + ((((size_t)parity * DP + p.rank) * p.n_tiles + e.tile) * rpo + (row - owner * rpo)) * 17 + j;
                 if (j < 16) st_ll(dst, own[row * kOwnLd + 2 * j], own[row * kOwnLd + 2 * j + 1], epoch);
                 else st_ll(dst, own[row * kOwnLd + 32], 0.f, epoch);
             }
         }
 
-        // ---------------- phase B: reduce the rows I own in rank order, SGD, publish the new weights
+        // ---------------- phase B: reduce the rows I own in rank order, SGD, publish the new weights.
+        // Every thread owns up to kLB lines; ALL polls and weight loads of the batch are issued before the first wait -
+        // a line-by-line loop pays one L2 round trip per poll plus one per weight load (measured: 9 us at dp = 2).
+        if (e.gate_w != nullptr) {
+            // the update overwrites W_l in place: the chain kernel's dgrad of this layer must have consumed it
+            if (etid == 0) wait_counter_ge_gpu(e.gate_w, e.gate_mult * ld_acquire_gpu(p.gate_step));
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         {
+            constexpr int kLB = (rpo * 17 + 127) / 128;          // dp 2: 9, dp 4: 5, dp 8: 3
             const int my_rows = max(0, min(rpo, rows_valid - p.rank * rpo));
             const int n_lines = my_rows * lpr;
-            for (int idx = etid; idx < n_lines; idx += 128) {
-                const int r = idx / lpr, j = idx - r * lpr;
-                uint4 ln[kMaxDp];
+            const float* mine0 = own + (p.rank * rpo) * kOwnLd;
+            const uint4* zoneA = p.llA[p.rank] + (size_t)parity * DP * p.n_tiles * rpo * 17;
+            for (int i0 = etid; i0 < n_lines; i0 += 128 * kLB) {
+                uint4 ln[kLB][DP];
+                float wv0[kLB], wv1[kLB];
 #pragma unroll
-                for (int s = 0; s < kMaxDp; ++s)
-                    if (s < p.dp && s != p.rank)
-                        ln[s] = ld_ll(p.llA[p.rank] + ((((size_t)parity * p.dp + s) * p.n_tiles + e.tile) * rpo + r) * 17 + j);
-                float s0 = 0.f, s1 = 0.f;
+                for (int u = 0; u < kLB; ++u) {
+                    const int idx = i0 + 128 * u;
+                    if (idx >= n_lines) continue;
+                    const int r = idx / lpr, j = idx - r * lpr;
 #pragma unroll
-                for (int s = 0; s < kMaxDp; ++s) {
-                    if (s >= p.dp) continue;
-                    float a, b;
-                    if (s == p.rank) {
-                        const float* mine = own + (p.rank * rpo + r) * kOwnLd;
-                        a = mine[j < 16 ? 2 * j : 32];
-                        b = j < 16 ? mine[2 * j + 1] : 0.f;
-                    } else {
-                        const uint4 x = wait_ll(p.llA[p.rank] + ((((size_t)parity * p.dp + s) * p.n_tiles + e.tile) * rpo + r) * 17 + j, ln[s], epoch);
-                        a = __uint_as_float(x.x);
-                        b = __uint_as_float(x.z);
+                    for (int sr = 0; sr < DP; ++sr)
+                        if (sr != p.rank) ln[u][sr] = ld_ll(zoneA + (((size_t)sr * p.n_tiles + e.tile) * rpo + r) * 17 + j);
+                    const float* wrow = p.W + e.w_offset + (int64_t)(e.m0 + p.rank * rpo + r) * e.ldw;
+                    const int n = j < 16 ? e.n0 + 2 * j : e.n_total;
+                    wv0[u] = (j == 16 || n < e.n_total) ? wrow[n] : 0.f;
+                    wv1[u] = (j < 16 && n + 1 < e.n_total) ? wrow[n + 1] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kLB; ++u) {
+                    const int idx = i0 + 128 * u;
+                    if (idx >= n_lines) continue;
+                    const int r = idx / lpr, j = idx - r * lpr;
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int sr = 0; sr < DP; ++sr) {
+                        float a, b;
+                        if (sr == p.rank) {
+                            a = mine0[r * kOwnLd + (j < 16 ? 2 * j : 32)];
+                            b = j < 16 ? mine0[r * kOwnLd + 2 * j + 1] : 0.f;
+                        } else {
+                            const uint4 x = wait_ll(zoneA + (((size_t)sr * p.n_tiles + e.tile) * rpo + r) * 17 + j, ln[u][sr], epoch);
+                            a = __uint_as_float(x.x);
+                            b = __uint_as_float(x.z);
+                        }
+                        s0 = (sr == 0) ? a : s0 + a;             // fixed order 0, 1, .., dp-1: deterministic
+                        s1 = (sr == 0) ? b : s1 + b;
                     }
-                    s0 = (s == 0) ? a : s0 + a;                  // fixed order 0, 1, .., dp-1: deterministic
-                    s1 = (s == 0) ? b : s1 + b;
-                }
-                const int row = p.rank * rpo + r;                // row inside the tile
-                float* wrow = p.W + e.w_offset + (int64_t)(e.m0 + row) * e.ldw;
-                float w0 = 0.f, w1 = 0.f;
-                if (j < 16) {
-                    const int n = e.n0 + 2 * j;
-                    if (n < e.n_total) { w0 = wrow[n] - p.lr * s0; wrow[n] = w0; }
-                    if (n + 1 < e.n_total) { w1 = wrow[n + 1] - p.lr * s1; wrow[n + 1] = w1; }
-                } else {
-                    w0 = wrow[e.n_total] - p.lr * s0;            // bias lives in column `in` of the block
-                    wrow[e.n_total] = w0;
-                }
+                    const int row = p.rank * rpo + r;            // row inside the tile
+                    float* wrow = p.W + e.w_offset + (int64_t)(e.m0 + row) * e.ldw;
+                    float w0 = 0.f, w1 = 0.f;
+                    if (j < 16) {
+                        const int n = e.n0 + 2 * j;
+                        if (n < e.n_total) { w0 = wv0[u] - p.lr * s0; wrow[n] = w0; }
+                        if (n + 1 < e.n_total) { w1 = wv1[u] - p.lr * s1; wrow[n + 1] = w1; }
+                    } else {
+                        w0 = wv0[u] - p.lr * s0;                 // bias lives in column `in` of the block
+                        wrow[e.n_total] = w0;
+                    }
 #pragma unroll
-                for (int d = 0; d < kMaxDp; ++d)
-                    if (d < p.dp && d != p.rank)
-                        st_ll(p.llC[d] + (((size_t)parity * p.n_tiles + e.tile) * kBlockM + row) * 17 + j, w0, w1, epoch);
+                    for (int d = 0; d < DP; ++d)
+                        if (d != p.rank) st_ll(p.llC[d] + (((size_t)parity * p.n_tiles + e.tile) * kBlockM + row) * 17 + j, w0, w1, epoch);
+                }
             }
         }
 
@@ -312,7 +335,7 @@ size_t dp_ll_zone_lines(int dp, int n_tiles) { return (size_t)2 * n_tiles * kBlo
 const char* dp_ll_plan(DpLLPlan* plan, const DpLLLayer* layers, int n_layers, int rows, const DpLLParams& base) {
     *plan = DpLLPlan{};
     plan->p = base;
-    if (base.dp < 2 || base.dp > kMaxDp || ((int)kBlockM % base.dp) != 0) return "dp_ll_plan: dp must divide 128 and be in [2, 8]";
+    if (base.dp != 2 && base.dp != 4 && base.dp != 8) return "dp_ll_plan: dp must be 2, 4 or 8";
     std::vector<DpLLEntry> host;
     int tile = 0;
     bool split = false;
@@ -340,7 +363,7 @@ const char* dp_ll_plan(DpLLPlan* plan, const DpLLLayer* layers, int n_layers, in
                 e.has_bias = nt == 0 ? 1 : 0;
                 e.tile = tile++;
                 e.w_offset = ly.w_offset; e.ldw = ly.ldw;
-                e.gate_flag = ly.gate_flag; e.gate_mult = ly.gate_mult;
+                e.gate_flag = ly.gate_flag; e.gate_w = ly.gate_w; e.gate_mult = ly.gate_mult;
                 host.push_back(e);
             }
     }
@@ -368,10 +391,20 @@ void dp_ll_free(DpLLPlan* plan) {
     plan->entries_dev = nullptr;
 }
 
-cudaError_t dp_ll_configure() { return cudaFuncSetAttribute(dp_ll_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); }
+cudaError_t dp_ll_configure() {
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(dp_ll_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(dp_ll_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return err;
+    return cudaFuncSetAttribute(dp_ll_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+}
 
 cudaError_t launch_dp_ll(const DpLLPlan& plan, cudaStream_t stream) {
-    dp_ll_wgrad_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev, plan.p);
+    switch (plan.p.dp) {
+        case 2: dp_ll_wgrad_kernel<2><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev, plan.p); break;
+        case 4: dp_ll_wgrad_kernel<4><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev, plan.p); break;
+        case 8: dp_ll_wgrad_kernel<8><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.entries_dev, plan.p); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -162,7 +162,8 @@ struct DpLLEntry {               // one CTA = one [128 x 32] tile of one layer's
     int tile;                    // index in the landing zones
     int64_t w_offset;            // float offset of the layer's [out, ld] block in the arena
     int ldw;
-    const uint32_t* gate_flag;   // chain-kernel counter this tile waits for (nullptr: ordered by the stream instead)
+    const uint32_t* gate_flag;   // chain-kernel counter the GEMM waits for: dz[l] final (nullptr: ordered by the stream instead)
+    const uint32_t* gate_w;      // counter the in-place weight update waits for: dgrad of layer l consumed W_l (nullptr: none)
     uint32_t gate_mult;
 };
 struct DpLLParams {
@@ -180,6 +181,7 @@ struct DpLLLayer {
     int lddz, ldx, in, out, ldw;
     int64_t w_offset;
     const uint32_t* gate_flag;
+    const uint32_t* gate_w;
     uint32_t gate_mult;
 };
 struct DpLLPlan {

@@ -719,8 +719,8 @@ void PipeEngine::build_coalesced() {
     const bool chain = chain_ok_;
     // Gated launch: the LL data-parallel kernel (dp_ll.cu) is forked at the START of the step next to the chain kernel
     // instead of behind it.  The chain kernel's epilogue warps count up a per-layer device counter when dz[l] is
-    // globally visible; the tiles of layer l wait for ready[l-1] (dz[l] final AND the dgrad that reads W_l retired -
-    // W_l is updated in place) before their first TMA load.  Only the last layers' tiles remain behind the chain kernel.
+    // globally visible; the tiles of layer l wait for ready[l] before their first TMA load and for ready[l-1] (the dgrad
+    // that reads W_l retired) before they update W_l in place.  Only layer 1's tiles remain behind the chain kernel.
     // (The same gate in front of the single-GPU grouped wgrad launch was measured neutral - 79.7 vs 78.7 us - and removed.)
     const bool group_env = getenv("SSB_WGRAD_GROUP") != nullptr && atoi(getenv("SSB_WGRAD_GROUP")) > 0;
     auto env_on = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) > 0 : dflt; };
@@ -809,7 +809,13 @@ void PipeEngine::build_coalesced() {
             ly.dZ = dz_all_[l]; ly.X = act_all_[l - 1];
             ly.dZ_lo = cfg_.split ? dz_lo_all_[l] : nullptr; ly.X_lo = cfg_.split ? act_lo_all_[l - 1] : nullptr;
             ly.lddz = act_ld_[l]; ly.ldx = act_ld_[l - 1]; ly.in = ls.in; ly.out = ls.out; ly.ldw = ls.ld; ly.w_offset = ls.offset;
-            if (gate_on_) { ly.gate_flag = gate_ready_ + (l >= 2 ? l - 1 : 1); ly.gate_mult = 8u * (uint32_t)M; }
+            if (gate_on_) {
+                // GEMM + reduce-scatter hop start when dz[l] is final; the in-place update of W_l additionally waits until
+                // the dgrad that reads W_l has produced dz[l-1] (layer 1 of the first stage has no dgrad)
+                ly.gate_flag = gate_ready_ + l;
+                ly.gate_w = l >= 2 ? gate_ready_ + (l - 1) : nullptr;
+                ly.gate_mult = 8u * (uint32_t)M;
+            }
             ll_layers.push_back(ly);
             continue;
         }
