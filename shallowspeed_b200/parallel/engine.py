@@ -83,10 +83,17 @@ def serve_fd_finish(srv, path: str, fd: int, n_peers: int):
     import os
     import socket
 
+    import struct
+
     try:
         for _ in range(n_peers):
             conn, _addr = srv.accept()
             with conn:
+                # only processes of the same user may receive the multicast handle
+                cred = conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+                _pid, uid, _gid = struct.unpack("3i", cred)
+                if uid != os.getuid():
+                    raise PermissionError(f"NVLS fd exchange: connection from uid {uid}, expected {os.getuid()}")
                 socket.send_fds(conn, [b"ssb-nvls"], [fd])
     finally:
         srv.close()
@@ -134,14 +141,19 @@ def make_nvls_context(comm: Comm, model, lr: float):
     leader = comm.rank == 0
     box = [None]
     srv = fd = None
+    sock_dir = None
     if leader:
+        import tempfile
+
         fd = ctx.export_fd()
-        box[0] = f"/tmp/ssb_nvls_{os.getpid()}_{comm.ranks[0]}.sock"
+        sock_dir = tempfile.mkdtemp(prefix="ssb_nvls_")  # mode 0700, unpredictable name: no symlink / squatting games in /tmp
+        box[0] = os.path.join(sock_dir, "fd.sock")
         srv = serve_fd(box[0], fd, comm.size - 1)       # listening BEFORE the path is announced
     dist.broadcast_object_list(box, src=comm.ranks[0], group=comm.group)
     if leader:
         serve_fd_finish(srv, box[0], fd, comm.size - 1)
         os.close(fd)
+        os.rmdir(sock_dir)
     else:
         got = recv_fd(box[0])
         ctx.import_fd(got)

@@ -23,8 +23,26 @@ def test_train_sequential_cpu(tmp_path):
     recs = [json.loads(l) for l in open(log)]
     assert any(rec.get("event") == "epoch" and rec["steps"] == 6 for rec in recs)
     assert (tmp_path / "ck" / "stage0of1.pt").exists()
-    r2 = _run(["train.py", "--device", "cpu", "--steps", "2", "--no-eval", "--synthetic", "--resume", str(tmp_path / "ck")])
-    assert r2.returncode == 0, r2.stderr[-2000:]
+
+
+def test_resume_continues_the_same_run(tmp_path):
+    """6 steps in one go == 4 steps, checkpoint, resume to step 6: same global step, same position in the data, same
+    weights (the CPU path is bit-deterministic); a resume under a different learning rate is refused."""
+    import torch
+
+    base = ["train.py", "--device", "cpu", "--no-eval", "--synthetic"]
+    r = _run(base + ["--steps", "6", "--save", str(tmp_path / "full")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = _run(base + ["--steps", "4", "--save", str(tmp_path / "part")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = _run(base + ["--steps", "6", "--resume", str(tmp_path / "part"), "--save", str(tmp_path / "resumed")])
+    assert r.returncode == 0, r.stderr[-2000:]
+    a = torch.load(tmp_path / "full" / "stage0of1.pt")
+    b = torch.load(tmp_path / "resumed" / "stage0of1.pt")
+    assert a["step"] == b["step"] == 6 and a["hparams"] == b["hparams"]
+    assert torch.equal(a["weights"], b["weights"])
+    r = _run(base + ["--steps", "6", "--resume", str(tmp_path / "part"), "--lr", "0.5"])
+    assert r.returncode != 0 and "checkpoint was written with lr" in (r.stderr + r.stdout)
 
 
 def test_train_accepts_reference_flags_and_pipedream():

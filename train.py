@@ -162,10 +162,13 @@ def main(args):
                 verbose=(grid.rank == 0 or is_last))
     model.to(device)
     model.train()
+    hparams = {"lr": float(args.lr), "global_batch_size": int(args.global_batch_size), "seed_mode": str(args.seed_mode),
+               "n_mubatches": int(args.n_mubatches)}
+    resumed_step = 0
     if args.resume:
         from shallowspeed_b200.utils.checkpoint import load_stage
 
-        load_stage(model, args.resume, pp_comm.Get_rank(), args.pp)
+        resumed_step = load_stage(model, args.resume, pp_comm.Get_rank(), args.pp, expect_hparams=hparams)
     optimizer = SGD(model.parameters(), lr=args.lr, arena=model.arena)
 
     dataset = Dataset(save_dir, global_batch_size=args.global_batch_size,
@@ -192,8 +195,10 @@ def main(args):
     n_batches = dataset.get_num_batches()
     total_steps = args.steps if args.steps is not None else args.epochs * n_batches
     start_time = time.time()
-    step = 0
-    epoch = 0
+    # a resumed run continues where the checkpoint stopped: same global step, same position in the data
+    step = min(resumed_step, total_steps)
+    epoch = step // n_batches
+    first_batch = step % n_batches
     # the schedule is identical for every batch: build it once (the reference rebuilds
     # a Python object per batch, train.py:140-144)
     schedule = sched_cls(num_micro_batches=args.n_mubatches, num_stages=args.pp, stage_id=pp_comm.Get_rank())
@@ -207,10 +212,11 @@ def main(args):
                     logger.log(event="eval", epoch=epoch, step=step, accuracy=accuracy,
                                time_s=time.time() - start_time)
         t_epoch = time.time()
-        steps_this_epoch = min(n_batches, total_steps - step)
-        for batch_id in range(steps_this_epoch):
+        steps_this_epoch = min(n_batches - first_batch, total_steps - step)
+        for batch_id in range(first_batch, first_batch + steps_this_epoch):
             worker.execute(schedule, batch_id)
             step += 1
+        first_batch = 0
         if engine == "native":
             from shallowspeed_b200.parallel.engine import watchdog_seconds
 
@@ -237,7 +243,7 @@ def main(args):
         from shallowspeed_b200.utils.checkpoint import save_stage
 
         if dp_comm.Get_rank() == 0:
-            save_stage(model, args.save, pp_comm.Get_rank(), args.pp, step=step)
+            save_stage(model, args.save, pp_comm.Get_rank(), args.pp, step=step, hparams=hparams)
     logger.close()
     if args.dp * args.pp > 1:
         import torch.distributed as dist
