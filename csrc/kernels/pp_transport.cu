@@ -27,6 +27,21 @@ __global__ void __launch_bounds__(256) pp_push_kernel(const float4* __restrict__
     }
 }
 
+// Boundary tiles of narrow stages are a few KB: one CTA, no cross-CTA completion counter - so any number of these may be
+// in flight at once, each on the stream of the micro-batch that produced its tile.
+__global__ void __launch_bounds__(256) pp_push_small_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int n4,
+                                                            uint32_t* flag_peer, const uint32_t* credit_local, const uint32_t* epoch_ptr) {
+    const uint32_t epoch = *epoch_ptr;
+    if (threadIdx.x == 0) wait_flag_ge(credit_local, epoch - 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                            // cumulative: the CTA's stores are ordered before the flag
+        st_relaxed_sys(flag_peer, epoch);
+    }
+}
+
 __global__ void pp_wait_kernel(const uint32_t* flag_local, const uint32_t* epoch_ptr) {
     if (threadIdx.x == 0) wait_flag_ge(flag_local, *epoch_ptr);
 }
@@ -44,6 +59,11 @@ cudaError_t launch_pp_push(const float* src, float* dst_peer, int64_t n, uint32_
                            const uint32_t* epoch, uint32_t* done_counter, cudaStream_t stream) {
     if (n % 4 != 0) return cudaErrorInvalidValue;
     const int64_t n4 = n / 4;
+    if (n4 <= kPpSmallTileF4) {
+        pp_push_small_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst_peer), (int)n4,
+                                                    flag_peer, credit_local, epoch);
+        return cudaGetLastError();
+    }
     int64_t ctas = (n4 + 256 * 4 - 1) / (256 * 4);
     if (ctas < 1) ctas = 1;
     if (ctas > 32) ctas = 32;

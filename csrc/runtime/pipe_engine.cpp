@@ -37,7 +37,7 @@ static constexpr int kFusedDpMaxCtas = 120;
 
 PipeEngine::PipeEngine(const EngineConfig& cfg, float* weights, float* grads, int64_t arena_numel)
     : cfg_(cfg), W_(weights), G_(grads), arena_numel_(arena_numel), L_((int)cfg.layers.size()) {
-    n_mu_streams_ = std::max(1, std::min(cfg_.n_mu, 4));
+    n_mu_streams_ = std::max(1, std::min(cfg_.n_mu, 8));   // one stream per micro-batch in flight (GPipe with 8 micro-batches: all 8)
     n_w_streams_ = std::max(1, std::min(L_, 8));        // one stream per layer's wgrad when possible
     if (const char* e = getenv("SSB_MU_STREAMS")) n_mu_streams_ = std::max(1, std::min(atoi(e), std::max(1, cfg_.n_mu)));
     if (const char* e = getenv("SSB_W_STREAMS")) n_w_streams_ = std::max(1, atoi(e));
@@ -404,7 +404,12 @@ void PipeEngine::plan_per_mubatch() {
         if (pp_ctx_ && opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
             // ---- peer-memory transport: pushes first (one-sided: they never wait for the peer's schedule position,
             // only for the credit of the previous step), then the waits for what this group receives
-            use(s_comm_);
+            // Small boundary tiles (<= 32 KB: one-CTA push kernel, no shared completion counter) travel on the stream of
+            // their micro-batch: the push sits right behind the kernel that produced the tile and the flag wait right in
+            // front of the kernel that consumes it - no hop through a shared communication stream, micro-batches do not
+            // serialise on each other.  Bigger tiles keep the multi-CTA push on the communication stream.
+            const bool act_small = (int64_t)mb * act_ld_[L_] / 4 <= kPpSmallTileF4;
+            const bool dz_small = (int64_t)mb * act_ld_[0] / 4 <= kPpSmallTileF4;
             std::vector<std::pair<int, int>> recvs;  // (mu, is_act)
             std::vector<Op> waits;
             int j = i;
@@ -415,33 +420,39 @@ void PipeEngine::plan_per_mubatch() {
                 Op x;
                 x.stream = s_comm_; x.mu = mu;
                 if (o == I_SEND_ACT) {
-                    if (ev_fwd[mu] >= 0) emit_wait(s_comm_, ev_fwd[mu]);
+                    x.stream = act_small ? sm(mu) : s_comm_;
+                    use(x.stream);
+                    if (ev_fwd[mu] >= 0) emit_wait(x.stream, ev_fwd[mu]);
                     x.kind = OP_PP_PUSH; x.a = act_[mu][L_]; x.b = pp_ctx_->next_act_in(mu); x.n = (int64_t)mb * act_ld_[L_];
                     x.c = reinterpret_cast<float*>(pp_ctx_->next_act_arrived(mu));
                     x.d = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->act_credit()));
                     if (!x.b) throw std::runtime_error("PipeEngine: SendActivations without a successor mapping");
                     ops_.push_back(x);
                 } else if (o == I_SEND_GRAD) {
-                    if (ev_bwd[mu] >= 0) emit_wait(s_comm_, ev_bwd[mu]);
+                    x.stream = dz_small ? sm(mu) : s_comm_;
+                    use(x.stream);
+                    if (ev_bwd[mu] >= 0) emit_wait(x.stream, ev_bwd[mu]);
                     x.kind = OP_PP_PUSH; x.a = dz_[mu][0]; x.b = pp_ctx_->prev_dz_in(mu); x.n = (int64_t)mb * act_ld_[0];
                     x.c = reinterpret_cast<float*>(pp_ctx_->prev_dz_arrived(mu));
                     x.d = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->dz_credit()));
                     if (!x.b) throw std::runtime_error("PipeEngine: SendInputGrad without a predecessor mapping");
                     ops_.push_back(x);
                 } else if (o == I_RECV_ACT) {
+                    x.stream = sm(mu);                       // the wait is a one-warp kernel: always on the consumer's stream
                     x.kind = OP_PP_WAIT; x.a = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->act_arrived(mu)));
                     waits.push_back(x);
                     recvs.push_back({mu, 1});
                 } else {
+                    x.stream = sm(mu);
                     x.kind = OP_PP_WAIT; x.a = reinterpret_cast<float*>(const_cast<uint32_t*>(pp_ctx_->dz_arrived(mu)));
                     waits.push_back(x);
                     recvs.push_back({mu, 0});
                 }
             }
-            for (auto& w : waits) ops_.push_back(w);
-            if (!recvs.empty()) {
-                const int ev = emit_record(s_comm_);
-                for (auto& r : recvs) (r.second ? ev_in : ev_gout)[r.first] = ev;
+            for (size_t w = 0; w < waits.size(); ++w) {
+                use(waits[w].stream);
+                ops_.push_back(waits[w]);
+                (recvs[w].second ? ev_in : ev_gout)[recvs[w].first] = emit_record(waits[w].stream);
             }
             i = j;
             continue;

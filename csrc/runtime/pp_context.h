@@ -66,6 +66,8 @@ private:
 
 // kernels (csrc/kernels/pp_transport.cu)
 // push: wait until credit >= epoch-1, copy n floats (multiple of 4) to the peer slot, fence, raise the peer's flag to epoch
+// tiles of at most this many float4 (32 KB) are pushed by ONE CTA without a completion counter: safe to run concurrently
+static constexpr int64_t kPpSmallTileF4 = 2048;
 cudaError_t launch_pp_push(const float* src, float* dst_peer, int64_t n, uint32_t* flag_peer, const uint32_t* credit_local,
                            const uint32_t* epoch, uint32_t* done_counter, cudaStream_t stream);
 // wait: spin (bounded) until *flag_local >= epoch
