@@ -59,6 +59,14 @@ __device__ __forceinline__ uint4 wait_ll(const uint4* p, uint4 v, uint32_t epoch
     return v;
 }
 
+__device__ __forceinline__ unsigned long long gtime_ll() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// optional phase timeline (SSB_CHAIN_TIMELINE=1): 8 stamps per tile, written by the tile's first epilogue thread
+#define LLDBG(i) do { if (p.dbg != nullptr && etid == 0 && e.tile < 28) p.dbg[8 * e.tile + (i)] = gtime_ll(); } while (0)
+
 template <int DP>
 __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntry* __restrict__ entries, const DpLLParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -167,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
         const int rows_valid = min((int)kBlockM, e.m_total - e.m0);
         float* own = reinterpret_cast<float*>(smem_gen + own_off);
 
+        LLDBG(0);                                                // CTA resident, waiting for operands
         // bias gradient of my row: column sum of dZ over the local rows, read from the staged A panels
         float dbsum = 0.f;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -185,8 +194,10 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar(s));
         }
+        LLDBG(1);                                                // all operand tiles landed (gate open + TMA)
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        LLDBG(2);                                                // accumulator complete
         float v[32];
         {
             float a[16], b[16];
@@ -216,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
             }
         }
 
+        LLDBG(3);                                                // phase A lines issued
         // ---------------- phase B: reduce the rows I own in rank order, SGD, publish the new weights.
         // Every thread owns up to kLB lines; ALL polls and weight loads of the batch are issued before the first wait -
         // a line-by-line loop pays one L2 round trip per poll plus one per weight load (measured: 9 us at dp = 2).
@@ -284,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
             }
         }
 
+        LLDBG(4);                                                // my rows reduced, updated and published
         // ---------------- phase C: rows owned by other replicas: their new weights arrive as LL lines (coalesced polls,
         // a batch of loads in flight per thread before the first wait)
         {
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
                 }
             }
         }
+        LLDBG(5);                                                // all replicas' rows written locally
     }
     __syncthreads();
     if (warp == 1) {

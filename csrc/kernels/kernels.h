@@ -175,6 +175,7 @@ struct DpLLParams {
     float* W;                    // local weight arena
     uint4* llA[kMaxDp];          // reduce-scatter landing zones  [parity][src][tile][128 / dp rows][17 lines]
     uint4* llC[kMaxDp];          // all-gather landing zones      [parity][tile][128 rows][17 lines]
+    unsigned long long* dbg;     // optional phase timeline: 8 globaltimer stamps per tile (first 28 tiles)
 };
 struct DpLLLayer {
     const float *dZ, *X, *dZ_lo, *X_lo;

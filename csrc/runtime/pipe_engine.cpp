@@ -884,6 +884,14 @@ void PipeEngine::build_coalesced() {
         // deepest layer first: its tiles get the lowest block indices, i.e. they are resident first and their gate opens first
         DpLLParams base = dp_ctx_->ll_params();
         base.gate_step = gate_on_ ? gate_step_ : nullptr;
+        if (getenv("SSB_CHAIN_TIMELINE")) {
+            if (!chain_dbg_) {
+                CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
+                CUDA_CHECK(cudaMemset(chain_dbg_, 0, 4 * 256 * sizeof(unsigned long long)));
+                owned_.push_back(chain_dbg_);
+            }
+            base.dbg = chain_dbg_ + 3 * 256;              // role 3 of the timeline buffer: 8 stamps x 28 tiles + spare
+        }
         DpLLPlan lp;
         check(dp_ll_plan(&lp, ll_layers.data(), (int)ll_layers.size(), rows, base));
         ll_plans_.push_back(lp);

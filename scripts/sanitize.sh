@@ -5,7 +5,7 @@
 # three standard passes.  Eager mode (--no-graph) so every launch is attributed; tiny step counts because
 # the tools slow kernels down by 10-100x (the device-side spin limit is 4 s).
 set -u
-ARGS="bench.py --steps 2 --warmup 1 --no-graph --pool-batches 4"
+ARGS="bench.py --steps 2 --warmup 3 --repeats 1 --no-alt --no-graph --pool-batches 4"
 for tool in memcheck racecheck synccheck; do
     echo "== compute-sanitizer --tool $tool"
     timeout 900 compute-sanitizer --tool $tool --print-limit 20 python $ARGS 2>&1 | grep -E "=========|ERROR SUMMARY" | head -40
