@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
     const uint32_t tmem_slot = tmem_full_bar + 8u;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + own_off + own_bytes + 8u * (2 * p.stages + 1));
-    constexpr uint32_t tmem_cols = 32;
+    const uint32_t tmem_cols = e.split ? 64u : 32u;
+    const uint32_t small_off = e.split ? 32u : 0u;           // second accumulator for the small 3xTF32 cross terms (ptx.cuh)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&e.tmA);
@@ -148,9 +149,10 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
                     const uint32_t al = a_lo + (half_bytes >> 4), bl = b_lo + (half_bytes >> 4);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        umma_tf32(tmem_base, umma_desc_pack(al + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, (kb | k4) != 0 ? 1u : 0u);
-                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(bl + k4 * 64u, mn_hi), idesc, 1u);
-                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, 1u);
+                        const uint32_t first = (kb | k4) != 0 ? 1u : 0u;
+                        umma_tf32(tmem_base + small_off, umma_desc_pack(al + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, first);
+                        umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(bl + k4 * 64u, mn_hi), idesc, 1u);
+                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, first);
                     }
                 } else {
 #pragma unroll
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
         float v[32];
         {
             float a[16], b[16];
-            tmem_ld16(taddr, a);
-            tmem_ld16(taddr + 16, b);
+            tmem_ld16_acc(taddr, small_off, a);
+            tmem_ld16_acc(taddr + 16, small_off, b);
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v[j] = a[j]; v[16 + j] = b[j]; }
         }

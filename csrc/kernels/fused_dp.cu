@@ -197,7 +197,8 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + tile_bytes_k + 8u * (2 * p.stages + 2));
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)p.block_n * (p.split ? 2u : 1u)) tmem_cols <<= 1;
+    const uint32_t small_off = p.split ? (uint32_t)p.block_n : 0u;   // second accumulator for the small 3xTF32 cross terms (ptx.cuh)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -269,10 +270,10 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             const uint32_t al = a_lo + (half_bytes >> 4), bl = b_lo + (half_bytes >> 4);
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
-                                umma_tf32(tmem_base, umma_desc_pack(al + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc,
-                                          (kb | k4) != 0 ? 1u : 0u);
-                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(bl + k4 * 64u, mn_hi), idesc, 1u);
-                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, 1u);
+                                const uint32_t first = (kb | k4) != 0 ? 1u : 0u;
+                                umma_tf32(tmem_base + small_off, umma_desc_pack(al + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, first);
+                                umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(bl + k4 * 64u, mn_hi), idesc, 1u);
+                                umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * 64u, mn_hi), umma_desc_pack(b_lo + k4 * 64u, mn_hi), idesc, first);
                             }
                         } else
 #pragma unroll
@@ -324,7 +325,7 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             uint8_t* tile = smem_gen + p.stages * stage_bytes;
             for (int c = 0; c < p.block_n; c += 16) {
                 float v[16];
-                tmem_ld16(taddr + c, v);
+                tmem_ld16_acc(taddr + c, small_off, v);
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4)
                     *reinterpret_cast<float4*>(tile + (size_t)m_local * pitch + (size_t)(c + 4 * g4) * 4) =

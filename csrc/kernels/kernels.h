@@ -225,6 +225,9 @@ struct ChainParams {
     int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
+    int sync_debug;                  // SSB_RACECHECK=1: an explicit named barrier among the epilogue warps per layer, so that
+                                     // compute-sanitizer's racecheck (which cannot see tcgen05.commit -> mbarrier ordering) can
+                                     // verify the reuse of the activation ping-pong tiles
     uint32_t* ready;                 // optional [n_layers + 1] device counters: every epilogue warp of every CTA adds 1 to
                                      // ready[l] once its part of dz[l] (and everything it wrote before) is globally visible
     unsigned long long* dbg;         // optional timeline buffer (3 roles x 256 globaltimer stamps), CTA 0 only

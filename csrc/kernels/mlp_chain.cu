@@ -86,8 +86,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
     const uint32_t tmem_slot = act_ready_bar + 8u;
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
+    // 3xTF32: up to 4 rotating main accumulators (long reductions only: layer 1) + one for the small cross terms, see ptx.cuh
+    constexpr int kTmemBudget = 512;
+    const int max_rot = SPLIT ? acc_rotation(1 << 20, N, kTmemBudget) : 1;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)N) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)N * (SPLIT ? (uint32_t)max_rot + 1u : 1u)) tmem_cols <<= 1;
+    const uint32_t small_off = SPLIT ? (uint32_t)N * (uint32_t)max_rot : 0u;
     // loss-head transpose scratch [N][kScratchLd] floats, behind the barriers (128 B further)
     const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
 
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     tc_fence_after();
                 }
                 if (lane == 0) DBG(1, 3 * gemm_i);
+                const int rot = SPLIT ? acc_rotation(nkb, N, kTmemBudget) : 1;
                 for (int kb0 = 0; kb0 < nkb; kb0 += p.kps, ++it) {
                     const int cnt = min(p.kps, nkb - kb0);
                     const int s = it % p.stages;
@@ -211,10 +216,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 const uint32_t bl_lo = b_lo + ((b_from_stage ? half_stage : lo_off) >> 4);
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4) {
-                                    umma_tf32(tmem_base, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
-                                              ((kb0 + j) | k4) != 0 ? 1u : 0u);
-                                    umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
-                                    umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id, 1u);
+                                    const int kb = kb0 + j;
+                                    const uint32_t main_acc = tmem_base + (uint32_t)(kb % rot) * (uint32_t)N;   // rotate the hi*hi chains
+                                    umma_tf32(tmem_base + small_off, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                              (kb | k4) != 0 ? 1u : 0u);
+                                    umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
+                                    umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                              (kb >= rot || k4 != 0) ? 1u : 0u);
                                 }
                             } else
 #pragma unroll
@@ -284,9 +292,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 const bool m_ok = m < ly.out;
                 const float bias = m_ok ? __ldg(p.W + ly.w_off + (int64_t)m * ly.ldw + ly.in) : 0.f;
                 const bool is_logits = (l == L) && p.do_loss;
+                const int rot_f = SPLIT ? acc_rotation((ly.in + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;   // as the MMA warp chose
                 mbar_wait(tmem_full_bar, tmem_waits & 1);
                 ++tmem_waits;
                 tc_fence_after();
+                if (p.sync_debug) asm volatile("bar.sync 2, 256;" ::: "memory");   // racecheck aid, see kernels.h
                 if (threadIdx.x == 64) DBG(2, 2 * (tmem_waits - 1));
                 const uint32_t dst = abuf0 + wbuf * abuf_bytes;
                 float* __restrict__ gout = p.act[l] + (int64_t)row0 * p.act_ld[l];
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     float keep[16];
                     for (int c = c_lo; c < c_hi; c += 16) {
                         float v[16];
-                        tmem_ld16(taddr + c, v);
+                        tmem_ld16_acc(taddr + c, small_off, v, rot_f, (uint32_t)N);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float x = v[j] + bias;
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     if (q == 0 && half == 0) {
                         for (int c = 0; c < N; c += 16) {
                             float v[16];
-                            tmem_ld16(taddr + c, v);
+                            tmem_ld16_acc(taddr + c, small_off, v, rot_f, (uint32_t)N);
                             if (m < C) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) scratch[(c + j) * kScratchLd + m] = v[j] + bias;
@@ -448,6 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             for (int l = L; l >= bwd_lo; --l) {
                 const ChainLayer& ly = p.layers[l - 1];
                 const bool m_ok = m < ly.in;                 // output feature of dgrad = input feature of layer l
+                const int rot_b = SPLIT ? acc_rotation((ly.out + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;
                 const bool mask_on = (l >= 2) && p.layers[l - 2].relu;
                 const float* __restrict__ yprev = p.act[l - 1] + (int64_t)row0 * p.act_ld[l - 1];
                 float* __restrict__ gprev = p.dz[l - 1] + (int64_t)row0 * p.act_ld[l - 1];
@@ -462,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 mbar_wait(tmem_full_bar, tmem_waits & 1);
                 ++tmem_waits;
                 tc_fence_after();
+                if (p.sync_debug) asm volatile("bar.sync 2, 256;" ::: "memory");   // racecheck aid, see kernels.h
                 if (threadIdx.x == 64) DBG(2, 2 * (tmem_waits - 1));
                 const uint32_t dst = abuf0 + wbuf * abuf_bytes;
                 const bool more = (l > bwd_lo);              // another dgrad consumes this tile
@@ -476,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         else mk[j] = (mask_on && m_ok && n < p.mb_rows) ? yprev[(int64_t)n * p.act_ld[l - 1] + m] : 1.f;
                     }
                     float v[16];
-                    tmem_ld16(taddr + c, v);
+                    tmem_ld16_acc(taddr + c, small_off, v, rot_b, (uint32_t)N);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int n = c + j;

@@ -139,6 +139,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 3xTF32 keeps TWO accumulators per tile: the hi*hi products go to the main one, the two small cross terms (lo*hi,
+// hi*lo; 2^-11 of the result) to a second one `small_off` columns further.  The tensor core's accumulate step truncates
+// (measured: error grows linearly with the number of accumulate steps, ~0.7 * n * 2^-24 relative), so keeping the small
+// terms out of the main chain cuts the steps that matter by 3x; the two are added here in fp32 (round to nearest).
+// small_off == 0: single accumulator (TF32 mode).
+// Long reductions additionally rotate the hi*hi products of successive k-blocks over `n_main` main accumulators
+// (`main_stride` columns apart): each chain is n_main times shorter; the partial sums are added here.
+__device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, uint32_t small_off, float (&v)[16], int n_main = 1, uint32_t main_stride = 0u) {
+    tmem_ld16(taddr, v);
+    for (int r = 1; r < n_main; ++r) {
+        float w[16];
+        tmem_ld16(taddr + (uint32_t)r * main_stride, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
+    }
+    if (small_off != 0u) {
+        float w[16];
+        tmem_ld16(taddr + small_off, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
+    }
+}
+// how many main accumulators a reduction over `nkb` k-blocks of a tile with `n_cols` columns uses inside a budget of
+// `budget_cols` TMEM columns (one more accumulator of the same width holds the small terms)
+__host__ __device__ __forceinline__ int acc_rotation(int nkb, int n_cols, int budget_cols) {
+    if (nkb < 8) return 1;
+    int r = budget_cols / n_cols - 1;
+    return r < 1 ? 1 : (r > 4 ? 4 : r);
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2), Blackwell version 1.
 //   K-major  operand tile [rows x 32 fp32]: rows are 128 B apart, 8-row groups 1024 B apart

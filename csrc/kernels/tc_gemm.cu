@@ -74,8 +74,12 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + epi_bytes + 8u * (2 * p.stages) + 8u);
 
+    // 3xTF32 accumulators (ptx.cuh): one for the small cross terms; FWD / DGRAD reductions over >= 8 k-blocks rotate the
+    // hi*hi products over up to 4 main accumulators, inside half of the TMEM columns.
+    const int rot = (p.split && MODE != GEMM_WGRAD) ? acc_rotation(num_kb, p.block_n, 256) : 1;   // 256 of 512 columns: two CTAs of this kernel may share an SM
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)p.block_n * (p.split ? (uint32_t)rot + 1u : 1u)) tmem_cols <<= 1;
+    const uint32_t small_off = p.split ? (uint32_t)p.block_n * (uint32_t)rot : 0u;
 
     const bool db_active = (MODE == GEMM_WGRAD) && (p.db != nullptr) && (by == 0);
 
@@ -165,12 +169,13 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                         const uint32_t al_lo = a_lo + (half_bytes >> 4), bl_lo = b_lo + (half_bytes >> 4);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            umma_tf32(tmem_base, umma_desc_pack(al_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
+                            const uint32_t main_acc = tmem_base + (uint32_t)(kb % rot) * (uint32_t)p.block_n;
+                            umma_tf32(tmem_base + small_off, umma_desc_pack(al_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
                                       idesc, (kb | k4) != 0 ? 1u : 0u);
-                            umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
+                            umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
                                       idesc, 1u);
-                            umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
-                                      idesc, 1u);
+                            umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
+                                      idesc, (kb >= rot || k4 != 0) ? 1u : 0u);
                         }
                     } else
 #pragma unroll
@@ -222,7 +227,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
             float* ws = p.partial + ((size_t)tile * p.k_splits + bz) * tile_floats;
             for (int c = 0; c < p.block_n; c += 16) {
                 float v[16];
-                tmem_ld16(taddr + c, v);
+                tmem_ld16_acc(taddr + c, small_off, v, rot, (uint32_t)p.block_n);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) __stcg(ws + (size_t)(c + j) * kBlockM + m_local, v[j]);   // lanes -> consecutive floats
             }
@@ -292,7 +297,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                     }
                 }
                 float v[16];
-                tmem_ld16(taddr + c, v);
+                tmem_ld16_acc(taddr + c, small_off, v, rot, (uint32_t)p.block_n);
                 if (!m_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -325,7 +330,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float v[16];
-                    tmem_ld16(taddr + pj * 32 + h * 16, v);
+                    tmem_ld16_acc(taddr + pj * 32 + h * 16, small_off, v);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t chunk = (uint32_t)(h * 4 + q) ^ ((uint32_t)m_local & 7u);

@@ -261,6 +261,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.inv_batch = 1.0f / (float)cfg_.global_batch;
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
+    cp.sync_debug = (getenv("SSB_RACECHECK") && atoi(getenv("SSB_RACECHECK")) > 0) ? 1 : 0;
     cp.ready = (gate_on_ && do_bwd && do_fwd) ? gate_ready_ : nullptr;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {

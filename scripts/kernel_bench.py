@@ -47,6 +47,24 @@ def time_fn(fn, iters, flush=None):
     return ts[len(ts) // 2]
 
 
+def time_rotating(fns, iters):
+    """Back-to-back launches cycling through `len(fns)` instances of the same op on DISTINCT operand buffers whose total
+    size is several times L2: every launch streams its weights from HBM (the previous launches evicted them) and the lines
+    it evicts are CLEAN.  The per-iteration "cold" mode above flushes L2 with a read-modify-write pass, i.e. it leaves up to
+    126 MB of dirty lines whose write-back competes with the timed kernel's reads (pessimistic by up to 1.47x for a 268 MB
+    weight matrix); this mode is what a real step of a model larger than L2 looks like."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="default", choices=["default", "stress", "all"])
@@ -66,8 +84,10 @@ def main():
     for rows, k, n in shapes:
         x = torch.randn(rows, k, device=dev)
         ld = (k + 1 + 7) // 8 * 8
-        Wb = torch.randn(n, ld, device=dev)
-        Gb = torch.zeros(n, ld, device=dev)
+        n_rot = max(1, min(4, int(3 * 126e6 // (n * ld * 4)) + 1)) if n * ld * 4 > 32e6 else 1   # >= 3 x L2 of distinct weights
+        Wbs = [torch.randn(n, ld, device=dev) for _ in range(n_rot)]
+        Gbs = [torch.zeros(n, ld, device=dev) for _ in range(n_rot)]
+        Wb, Gb = Wbs[0], Gbs[0]
         W, b = Wb[:, :k], Wb[:, k]
         y = K.empty_padded(rows, n, dev)
         dz = K.empty_padded(rows, n, dev)
@@ -85,14 +105,35 @@ def main():
             ks = args.k_splits
             cases["fwd_splitk"] = (lambda: K.linear_fwd(x, W, b, relu=True, out=y, precision=pr, k_splits=ks), cases["fwd"][1])
             cases["dgrad_splitk"] = (lambda: K.linear_dgrad(dz, W, mask=x, out=dx, precision=pr, k_splits=ks), cases["dgrad"][1])
+        def rot(name):
+            """the same op on each of the rotating weight / gradient buffers"""
+            out = []
+            for Wr, Gr in zip(Wbs, Gbs):
+                Wv, bv = Wr[:, :k], Wr[:, k]
+                ks = args.k_splits
+                out.append({
+                    "fwd": lambda Wv=Wv, bv=bv: K.linear_fwd(x, Wv, bv, relu=True, out=y, precision=pr),
+                    "dgrad": lambda Wv=Wv: K.linear_dgrad(dz, Wv, mask=x, out=dx, precision=pr),
+                    "wgrad_write": lambda Gr=Gr: K.linear_wgrad(dz, x, Gr[:, :k], accumulate=False, grad_b=Gr[:, k], precision=pr),
+                    "wgrad_acc": lambda Gr=Gr: K.linear_wgrad(dz, x, Gr[:, :k], accumulate=True, grad_b=Gr[:, k], precision=pr),
+                    "fwd_splitk": lambda Wv=Wv, bv=bv: K.linear_fwd(x, Wv, bv, relu=True, out=y, precision=pr, k_splits=ks),
+                    "dgrad_splitk": lambda Wv=Wv: K.linear_dgrad(dz, Wv, mask=x, out=dx, precision=pr, k_splits=ks),
+                }[name])
+            return out
+
         for name, (fn, nbytes) in cases.items():
             warm = time_fn(fn, args.iters)
             cold = time_fn(fn, max(10, args.iters // 3), flush=flush)
             flops = 2.0 * rows * k * n
-            print(json.dumps({"kernel": name, "rows": rows, "in": k, "out": n, "us_back_to_back": round(warm, 2),
-                              "us_cold_l2": round(cold, 2), "GBps_cold": round(nbytes / cold / 1e3, 1),
-                              "frac_hbm_measured": round(nbytes / cold / 1e3 / pk["hbm_gbs"], 3),
-                              "tflops_cold": round(flops / cold / 1e6, 2)}), flush=True)
+            rec = {"kernel": name, "rows": rows, "in": k, "out": n, "us_back_to_back": round(warm, 2),
+                   "us_cold_l2": round(cold, 2), "GBps_cold": round(nbytes / cold / 1e3, 1),
+                   "frac_hbm_measured": round(nbytes / cold / 1e3 / pk["hbm_gbs"], 3),
+                   "tflops_cold": round(flops / cold / 1e6, 2)}
+            if n_rot > 1:
+                stream = time_rotating(rot(name), max(12, args.iters))
+                rec.update({"us_stream": round(stream, 2), "GBps_stream": round(nbytes / stream / 1e3, 1),
+                            "frac_hbm_stream": round(nbytes / stream / 1e3 / pk["hbm_gbs"], 3), "rotating_buffers": n_rot})
+            print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":

@@ -86,13 +86,21 @@ def sass_census():
         census.append(f"| `{name[:70]}` | {c(r'UTCHMMA')} | {c(r'LDTM')} | {c(r'UTMALDG')} | {c(r'UTMASTG') + c(r'UTMAREDG')} | "
                       f"{c(r'UTCBAR')} | {c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'\.SYS') - c(r'MEMBAR\.[A-Z.]*SYS')} | {c(r'HMMA') - c(r'UTCHMMA')} | "
                       f"{c(r'\.MULTICAST')} | {c(r'LDGMC')} |")
-        if "tc_gemm_kernel" in name or "fused_wgrad_dp" in name:
+        if any(k in name for k in ("tc_gemm_kernel", "fused_wgrad_dp", "mlp_chain_kernel", "dp_ll_wgrad", "tc_wgrad_group", "nvls_reduce_sgd")):
             if "fused_wgrad_dp" in name:
                 short = "fused_wgrad_dp"
+            elif "mlp_chain_kernel" in name:
+                short = "mlp_chain_" + ("fp32" if "ILb1E" in name else "tf32")
+            elif "dp_ll_wgrad" in name:
+                short = "dp_ll_dp" + re.search(r"ILi(\d)E", name).group(1)
+            elif "tc_wgrad_group" in name:
+                short = "tc_wgrad_group"
+            elif "nvls_reduce_sgd" in name:
+                short = "nvls_reduce_sgd"
             else:
-                m = re.search(r"ILi(\d)E(?:Lb(\d)ELb(\d)E)?", name)
-                short = "tc_gemm_mode" + m.group(1) + ("_splitk" if m.group(2) == "1" else "") + ("_wlo" if m.group(3) == "1" else "")
-            keep = [ln for ln in f.split("\n") if re.search(r"UTC|LDTM|UTMA|SYNCS|MEMBAR|\.SYS|UBLKCP|ELECT|BAR\.", ln)]
+                m = re.search(r"ILi(\d)E(?:Lb(\d)E)?", name)
+                short = "tc_gemm_mode" + m.group(1) + ("_splitk" if m.group(2) == "1" else "")
+            keep = [ln for ln in f.split("\n") if re.search(r"UTC|LDTM|UTMA|SYNCS|MEMBAR|\.SYS|UBLKCP|ELECT|BAR\.|\.STRONG\.GPU|RED\.|LDGMC|MULTIMEM|FENCE", ln)]
             open(os.path.join(OUT, f"sass_{short}.txt"), "w").write(
                 f"// {name}\n// tensor-core / TMA / barrier / system-scope instructions only (full listing: cuobjdump -sass)\n" + "\n".join(keep) + "\n")
     open(os.path.join(OUT, "sass_census.md"), "w").write("\n".join(census) + "\n")
@@ -105,13 +113,17 @@ def kernel_bench_md():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     out = ["# GEMM family microbenchmark (CUDA events, L2 flushed between timed launches, median)", "",
            f"roofline denominators: HBM copy {peaks.get('hbm_gbs', 6650)} GB/s (of measured), bf16 {peaks.get('bf16_tflops', 1590)} TFLOP/s", "",
-           "| kernel | rows | in | out | us (cold L2) | GB/s | frac of measured HBM | TFLOP/s (tf32) |", "|---|---|---|---|---|---|---|---|"]
+           "`cold`: L2 flushed by a read-modify-write pass before every launch (leaves dirty lines: pessimistic).  `stream`: back-to-back launches "
+           "rotating over >= 3 x L2 of distinct weight buffers (what a step of a model larger than L2 looks like).", "",
+           "| kernel | rows | in | out | us (cold L2) | GB/s | frac of measured HBM | TFLOP/s (tf32) | us (stream) | GB/s (stream) | frac of measured HBM (stream) |",
+           "|---|---|---|---|---|---|---|---|---|---|---|"]
     for l in open(path):
         try:
             d = json.loads(l)
         except Exception:
             continue
-        out.append(f"| {d['kernel']} | {d['rows']} | {d['in']} | {d['out']} | {d['us_cold_l2']} | {d['GBps_cold']} | {d['frac_hbm_measured']} | {d['tflops_cold']} |")
+        out.append(f"| {d['kernel']} | {d['rows']} | {d['in']} | {d['out']} | {d['us_cold_l2']} | {d['GBps_cold']} | {d['frac_hbm_measured']} | {d['tflops_cold']} | "
+                   f"{d.get('us_stream', '')} | {d.get('GBps_stream', '')} | {d.get('frac_hbm_stream', '')} |")
     open(os.path.join(OUT, "kernel_bench.md"), "w").write("\n".join(out) + "\n")
 
 
