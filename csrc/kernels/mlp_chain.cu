@@ -293,6 +293,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 const float bias = m_ok ? __ldg(p.W + ly.w_off + (int64_t)m * ly.ldw + ly.in) : 0.f;
                 const bool is_logits = (l == L) && p.do_loss;
                 const int rot_f = SPLIT ? acc_rotation((ly.in + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;   // as the MMA warp chose
+                // loss head: the targets do not depend on the MMA - fetch this lane's row before waiting for the logits
+                // (the head is ONE warp on the critical path between the last forward and the first backward GEMM)
+                float tg_pre[16];
+                const bool head_pre = is_logits && q == 0 && half == 0 && ly.out <= 16;
+                if (head_pre) {
+                    const float* __restrict__ tgp = p.target + (int64_t)(row0 + lane) * p.ldt;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) tg_pre[k] = (k < ly.out && lane < p.mb_rows) ? __ldg(tgp + k) : 0.f;
+                }
                 mbar_wait(tmem_full_bar, tmem_waits & 1);
                 ++tmem_waits;
                 tc_fence_after();
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 float ssum = 0.f;
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    tgv[k] = (k < C && row_ok) ? __ldg(tg + k) : 0.f;
+                                    tgv[k] = (n == lane) ? tg_pre[k] : ((k < C && row_ok) ? __ldg(tg + k) : 0.f);
                                     ev[k] = (k < C) ? expf(zr[k] - gmax) : 0.f;
                                     ssum += ev[k];
                                 }

@@ -373,6 +373,14 @@ void PipeEngine::plan_per_mubatch() {
     auto sw = [&](int l) { return 1 + n_mu_streams_ + (l % n_w_streams_); };
 
     std::vector<int> ev_in(M, -1), ev_fwd(M, -1), ev_gout(M, -1), ev_bwd(M, -1);
+    // Deferred weight-gradient wave (narrow stages, chain kernel): a micro-batch's backward only runs the dgrad chain; the
+    // weight gradients of ALL micro-batches are computed at the optimizer step by ONE launch over all rows (k-blocks in
+    // micro-batch order, SGD fused; with data parallelism the LL two-shot kernel), instead of n_mu accumulating GEMMs per
+    // layer chained through memory (pp=2 GPipe with 8 micro-batches: 32 serialised wgrad launches on stage 0).  dz / act of
+    // every micro-batch live in their own rows of the stage's buffers until the step ends, for every schedule.
+    auto env_on = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) > 0 : dflt; };
+    const bool ll_ok = cfg_.dp_mode == 2 && dp_ctx_ != nullptr && dp_ctx_->ll_enabled();
+    const bool defer_wgrad = chain_ok_ && cfg_.training && (cfg_.dp_mode == 0 || ll_ok) && env_on("SSB_PP_DEFER_WGRAD", true);
     std::vector<bool> first_write(L_ + 1, true);
     std::vector<bool> sw_joined(streams_.size(), false);
     std::vector<int> ev_allreduce;
@@ -557,7 +565,7 @@ void PipeEngine::plan_per_mubatch() {
                     // the whole dgrad chain in one launch; then one wave of weight-gradient GEMMs
                     add_chain(s, mu, 1, false, false, true);
                     const int ev_dz_all = emit_record(s);
-                    for (int l = L_; l >= 1; --l) {
+                    for (int l = L_; l >= 1 && !defer_wgrad; --l) {
                         const LayerSpec& ls = cfg_.layers[l - 1];
                         const int w = sw(l);
                         use(w);
@@ -629,7 +637,7 @@ void PipeEngine::plan_per_mubatch() {
                     }
                 }
                 ev_bwd[mu] = emit_record(s);
-                if (final_bwd && cfg_.dp_mode == 2) {
+                if (final_bwd && cfg_.dp_mode == 2 && !defer_wgrad) {
                     // G is final: reduce across replicas + SGD + weight broadcast in ONE kernel per layer
                     // over peer memory.  W is rewritten, so every reader (all micro-batches) must be done.
                     if (!dp_ctx_) throw std::runtime_error("PipeEngine: dp_mode fused needs a DpContext");
@@ -653,6 +661,46 @@ void PipeEngine::plan_per_mubatch() {
                 break;
             }
             case I_OPT_STEP: {
+                if (defer_wgrad) {
+                    const int rows_all = M * mb;
+                    use(s_dp_);
+                    for (int m2 = 0; m2 < M; ++m2)           // every reader of W and every producer of dz is done
+                        if (ev_bwd[m2] >= 0) emit_wait(s_dp_, ev_bwd[m2]);
+                        else if (ev_fwd[m2] >= 0) emit_wait(s_dp_, ev_fwd[m2]);
+                    if (cfg_.dp_mode == 0) {
+                        std::vector<GemmPlan> grouped;
+                        for (int l = L_; l >= 1; --l) {
+                            const LayerSpec& ls = cfg_.layers[l - 1];
+                            GemmPlan g;
+                            check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows_all, ls.in,
+                                                  ls.out, 0, Gl(l) + ls.in, ls.ld, Wl(l), ls.ld, cfg_.lr, 1, lo_wgrad(l, -1)));
+                            grouped.push_back(g);
+                        }
+                        GemmGroupPlan gp;
+                        check(gemm_group_plan(&gp, grouped.data(), (int)grouped.size()));
+                        group_plans_.push_back(gp);
+                        Op go;
+                        go.kind = OP_WGRAD_GROUP; go.stream = s_dp_; go.gemm = (int)group_plans_.size() - 1;
+                        ops_.push_back(go);
+                    } else {
+                        std::vector<DpLLLayer> lls;
+                        for (int l = L_; l >= 1; --l) {
+                            const LayerSpec& ls = cfg_.layers[l - 1];
+                            DpLLLayer ly{};
+                            ly.dZ = dz_all_[l]; ly.X = act_all_[l - 1];
+                            ly.dZ_lo = cfg_.split ? dz_lo_all_[l] : nullptr; ly.X_lo = cfg_.split ? act_lo_all_[l - 1] : nullptr;
+                            ly.lddz = act_ld_[l]; ly.ldx = act_ld_[l - 1]; ly.in = ls.in; ly.out = ls.out; ly.ldw = ls.ld; ly.w_offset = ls.offset;
+                            lls.push_back(ly);
+                        }
+                        DpLLPlan lp;
+                        check(dp_ll_plan(&lp, lls.data(), (int)lls.size(), rows_all, dp_ctx_->ll_params()));
+                        ll_plans_.push_back(lp);
+                        Op lo;
+                        lo.kind = OP_DP_LL; lo.stream = s_dp_; lo.gemm = (int)ll_plans_.size() - 1;
+                        ops_.push_back(lo);
+                    }
+                    break;
+                }
                 if (cfg_.dp_mode == 2) break;            // the update already happened inside the fused kernels
                 {
                     use(s_dp_);

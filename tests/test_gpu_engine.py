@@ -120,8 +120,9 @@ def test_engine_per_microbatch_path_matches_cpu(sched, chain, monkeypatch):
     init = MLP(SIZES, 0, 1, 128)
     for p0, pc, pg in zip(init.parameters(), mc.parameters(), mg.parameters()):
         assert _frob(pg.data.cpu() - p0.data, pc.data - p0.data) < UPD_TOL["fp32"]
-    # chain: per micro-batch 1 fwd(+loss) chain + 1 bwd chain + 7 wgrad, + 1 SGD; layer-wise: 7 + 1 + 6 + 7 each
-    expect = 4 * (1 + 1 + 7) + 1 if chain else 4 * (7 + 6 + 7) + 4 + 1
+    # chain: per micro-batch 1 fwd(+loss) chain + 1 bwd chain, then ONE grouped wgrad + SGD launch over all micro-batches
+    # (deferred weight-gradient wave); layer-wise: 7 + 1 + 6 + 7 each, + 1 SGD
+    expect = 4 * (1 + 1) + 1 if chain else 4 * (7 + 6 + 7) + 4 + 1
     assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == expect + EXTRA["fp32"]
 
 
