@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
                         const int n = e.n0 + 2 * j;
                         if (n < e.n_total) { w0 = wv0[u] - p.lr * s0; wrow[n] = w0; }
                         if (n + 1 < e.n_total) { w1 = wv1[u] - p.lr * s1; wrow[n + 1] = w1; }
+                        if (p.W_lo != nullptr) {               // lo twins of the new weights ride along (no arena-wide split kernel)
+                            float* lrow = p.W_lo + e.w_offset + (int64_t)(e.m0 + row) * e.ldw;
+                            if (n < e.n_total) lrow[n] = tf32_lo(w0);
+                            if (n + 1 < e.n_total) lrow[n + 1] = tf32_lo(w1);
+                        }
                     } else {
                         w0 = wv0[u] - p.lr * s0;                 // bias lives in column `in` of the block
                         wrow[e.n_total] = w0;
@@ -327,6 +332,11 @@ __global__ void __launch_bounds__(kThreads, 1) dp_ll_wgrad_kernel(const DpLLEntr
                         const int n = e.n0 + 2 * jv[u];
                         if (n < e.n_total) wrow[n] = __uint_as_float(x.x);
                         if (n + 1 < e.n_total) wrow[n + 1] = __uint_as_float(x.z);
+                        if (p.W_lo != nullptr) {
+                            float* lrow = p.W_lo + e.w_offset + (int64_t)(e.m0 + rowv[u]) * e.ldw;
+                            if (n < e.n_total) lrow[n] = tf32_lo(__uint_as_float(x.x));
+                            if (n + 1 < e.n_total) lrow[n + 1] = tf32_lo(__uint_as_float(x.z));
+                        }
                     } else {
                         wrow[e.n_total] = __uint_as_float(x.x);
                     }

@@ -67,7 +67,7 @@ __device__ __forceinline__ float* stage_slot(const DpPeers& peers, const DpLayer
 // ---- phase B: the owner reduces one tile in rank order, applies SGD, publishes the weights
 // Executed by `nthreads` threads (tid in [0, nthreads)), all of which must call it.
 __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& p, const TileCoord& tc, uint32_t epoch,
-                                     int tid, int nthreads, int bar_id, int part = 0, int nparts = 1) {
+                                     int tid, int nthreads, int bar_id, int part = 0, int nparts = 1, bool publish = true) {
     const int me = p.rank;
     // wait until every replica's partial of this tile has landed in my staging memory
     if (tid < p.dp) wait_flag_ge(peers.arrive[me] + (int64_t)tid * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
@@ -148,7 +148,7 @@ __device__ void dp_owner_reduce_tile(const DpPeers& peers, const DpLayerParams& 
             else for (int r2 = 0; r2 < p.dp; ++r2) peers.W[r2][boff] = b;
         }
     }
-    if (p.one_shot) return;                               // nothing to publish, nobody waits
+    if (p.one_shot || !publish) return;                   // nothing to publish / the caller publishes all its tiles at once
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
     if (tid == 0) {
         __threadfence_system();                            // one cumulative fence after the CTA barrier
@@ -293,6 +293,7 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int etid = (warp - 2) * 32 + lane;                 // 0..127 among the epilogue threads
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         // ---------------- phase A: compute every tile, push the partial to its owner
+        const bool batch_flags = (num_tiles > (int)gridDim.x) && p.helpers <= 1;   // more than one tile per CTA
         if (etid == 0) DPDBG(0);
         int it = 0, tile_i = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
@@ -365,10 +366,23 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     stage_slot(peers, p, dst_rank, p.rank, tc.slot, epoch)[(int64_t)kBlockM * p.block_n + m_local] = dbsum;
                 }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (etid == 0) {
+            if (etid == 0 && !batch_flags) {
                 if (tile_i == 0) DPDBG(2);
                 __threadfence_system();                           // partial visible system-wide before the flag(s)
                 if (tile_i == 0) DPDBG(3);
+                for (int d = 0; d < n_dst; ++d) {
+                    const int dst_rank = p.one_shot ? d : tc.owner;
+                    st_relaxed_sys(peers.arrive[dst_rank] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
+                }
+            }
+        }
+        if (batch_flags && etid == 0) {
+            // several tiles per CTA (wide layers): ONE system fence for all pushes of this CTA, then all arrival flags -
+            // a fence per tile costs 4.4 us each and stalls the epilogue warps between tiles
+            __threadfence_system();
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(p, t);
+                const int n_dst = p.one_shot ? p.dp : 1;
                 for (int d = 0; d < n_dst; ++d) {
                     const int dst_rank = p.one_shot ? d : tc.owner;
                     st_relaxed_sys(peers.arrive[dst_rank] + (int64_t)p.rank * p.slots_per_src + p.slot_flag_base + tc.slot, epoch);
@@ -379,7 +393,20 @@ fused_wgrad_dp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (etid == 0) DPDBG(4);
         for (int t = cta; t < num_tiles; t += n_cta) {
             const TileCoord tc = tile_coord(p, t);
-            if (p.one_shot || tc.owner == p.rank) dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1, 0, p.helpers > 1 ? p.helpers : 1);
+            if (p.one_shot || tc.owner == p.rank)
+                dp_owner_reduce_tile(peers, p, tc, epoch, etid, 128, 1, 0, p.helpers > 1 ? p.helpers : 1, /*publish=*/!batch_flags);
+        }
+        if (batch_flags && !p.one_shot) {
+            // all owned tiles of this CTA are reduced and their new weights stored into every replica: one fence, all flags
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (etid == 0) {
+                __threadfence_system();
+                for (int t = cta; t < num_tiles; t += n_cta) {
+                    const TileCoord tc = tile_coord(p, t);
+                    if (tc.owner != p.rank) continue;
+                    for (int r2 = 0; r2 < p.dp; ++r2) st_relaxed_sys(peers.done[r2] + p.tile_flag_base + tc.t, epoch);
+                }
+            }
         }
         // ---------------- phase C: wait for the owners of my other tiles
         if (etid == 0) DPDBG(6);

@@ -42,6 +42,10 @@ struct GemmParams {
     int ldw;
     float lr;
     int fuse_sgd;
+    // fp32-equivalent mode: with W_lo set, the fused update is a direct read-modify-write of the W tile by the thread
+    // that owns the row (no smem staging, no TMA reduce-add) which also stores the lo twin of the NEW weights - the
+    // arena-wide split kernel after the optimizer step disappears.  Same [out, ldw] geometry as W; nullptr = TMA reduce-add.
+    float* W_lo;
     // fp32-equivalent mode (3xTF32): both operands come with a `lo` twin (x - trunc_tf32(x)); FWD/DGRAD
     // also emit the lo twin of their output so the next GEMM can consume it
     int split;
@@ -173,6 +177,7 @@ struct DpLLParams {
     const uint32_t* gate_step;   // steps of the launching engine (gate target = gate_mult * *gate_step)
     int n_tiles, stages;
     float* W;                    // local weight arena
+    float* W_lo;                 // optional: lo twins of the weights (3xTF32), refreshed by whoever stores a weight
     uint4* llA[kMaxDp];          // reduce-scatter landing zones  [parity][src][tile][128 / dp rows][17 lines]
     uint4* llC[kMaxDp];          // all-gather landing zones      [parity][tile][128 rows][17 lines]
     unsigned long long* dbg;     // optional phase timeline: 8 globaltimer stamps per tile (first 28 tiles)

@@ -674,6 +674,7 @@ void PipeEngine::plan_per_mubatch() {
                             GemmPlan g;
                             check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows_all, ls.in,
                                                   ls.out, 0, Gl(l) + ls.in, ls.ld, Wl(l), ls.ld, cfg_.lr, 1, lo_wgrad(l, -1)));
+                            if (cfg_.split) g.p.W_lo = W_lo_ + ls.offset;
                             grouped.push_back(g);
                         }
                         GemmGroupPlan gp;
@@ -693,7 +694,9 @@ void PipeEngine::plan_per_mubatch() {
                             lls.push_back(ly);
                         }
                         DpLLPlan lp;
-                        check(dp_ll_plan(&lp, lls.data(), (int)lls.size(), rows_all, dp_ctx_->ll_params()));
+                        DpLLParams base = dp_ctx_->ll_params();
+                        base.W_lo = cfg_.split ? W_lo_ : nullptr;
+                        check(dp_ll_plan(&lp, lls.data(), (int)lls.size(), rows_all, base));
                         ll_plans_.push_back(lp);
                         Op lo;
                         lo.kind = OP_DP_LL; lo.stream = s_dp_; lo.gemm = (int)ll_plans_.size() - 1;
@@ -732,7 +735,7 @@ void PipeEngine::plan_per_mubatch() {
         cr.b = cfg_.training ? reinterpret_cast<float*>(pp_ctx_->next_dz_credit()) : nullptr;
         ops_.push_back(cr);
     }
-    if (w_lo_needed_ && cfg_.training) {     // weights changed: refresh their lo twin for the next step
+    if (w_lo_needed_ && cfg_.training && !defer_wgrad) {   // weights changed: refresh their lo twin (the deferred wave's kernels do it themselves)
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -915,6 +918,9 @@ void PipeEngine::build_coalesced() {
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
+        // narrow stages (latency-bound): the update kernel read-modify-writes its tile and refreshes the lo twins itself;
+        // wide layers (bandwidth-bound) keep the TMA reduce-add + the arena-wide split kernel
+        if (fuse && cfg_.split && chain) g.p.W_lo = W_lo_ + ls.offset;
         if (group_wgrad) {                                  // launched together after the loop
             grouped.push_back(g);
             continue;
@@ -933,6 +939,7 @@ void PipeEngine::build_coalesced() {
         // deepest layer first: its tiles get the lowest block indices, i.e. they are resident first and their gate opens first
         DpLLParams base = dp_ctx_->ll_params();
         base.gate_step = gate_on_ ? gate_step_ : nullptr;
+        base.W_lo = cfg_.split ? W_lo_ : nullptr;          // owner rows and received rows refresh their lo twins
         if (getenv("SSB_CHAIN_TIMELINE")) {
             if (!chain_dbg_) {
                 CUDA_CHECK(cudaMalloc(&chain_dbg_, 4 * 256 * sizeof(unsigned long long)));
@@ -978,7 +985,10 @@ void PipeEngine::build_coalesced() {
     }
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
-    if (w_lo_needed_) {                      // weights changed: refresh their lo twin for the next step
+    // lo twins of the updated weights: written by the update kernels themselves (SGD-fused wgrad, LL data-parallel kernel);
+    // every other update path (NCCL / NVLS / flag-protocol kernels) is followed by the arena-wide split kernel
+    const bool wlo_in_update = (fuse && cfg_.split && chain) || !ll_layers.empty();
+    if (w_lo_needed_ && !wlo_in_update) {
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);

@@ -67,8 +67,9 @@ def _split(precision):
 
 
 def lo_twin(t: torch.Tensor) -> torch.Tensor:
-    """lo = t - trunc_tf32(t), same padded layout as t (t must be tma_ready)."""
-    base = torch.zeros(t.size(0), t.stride(0), dtype=torch.float32, device=t.device)
+    """lo = t - trunc_tf32(t), same padded layout as t (t must be tma_ready).  The split kernel writes the whole padded
+    storage (rows x pitch), so the buffer needs no memset: one kernel per twin, not two."""
+    base = torch.empty(t.size(0), t.stride(0), dtype=torch.float32, device=t.device)
     lo = base[:, : t.size(1)]
     assert lo.stride(0) == t.stride(0)
     _C.split_lo(t, lo)
