@@ -230,6 +230,21 @@ struct ChainParams {
     int mu_base;                     // first micro-batch handled by CTA 0 (per-micro-batch launches)
     float inv_batch;
     int do_fwd, do_loss, do_bwd, first_stage;
+    // Pipeline boundaries folded into the kernel (peer-memory transport, one launch = one micro-batch of a stage):
+    //  * in_flag  != nullptr: the tile this launch consumes (activations of the previous stage for a forward launch, output
+    //    gradients of the next stage for a backward launch) is final in local memory once *in_flag >= *pp_epoch; the
+    //    epilogue warps wait for it and stage the tile into shared memory - weights stream in meanwhile;
+    //  * x_from_global: forward launch of a stage > 0: the input tile is read from act[0] by the epilogue warps (after the
+    //    flag) instead of by TMA next to layer 1's weights, its lo twin is written to act_lo[0] on the way;
+    //  * out_peer != nullptr: the tile this launch produces for the neighbour (last forward output / dz[0]) is ALSO stored
+    //    into the neighbour's receive slot, then one system fence + *out_flag = epoch; *out_credit >= epoch - 1 (the
+    //    neighbour released its slots of the previous step) is awaited first.
+    const uint32_t* in_flag;
+    const uint32_t* pp_epoch;
+    int x_from_global;
+    float* out_peer;
+    uint32_t* out_flag;
+    const uint32_t* out_credit;
     int sync_debug;                  // SSB_RACECHECK=1: an explicit named barrier among the epilogue warps per layer, so that
                                      // compute-sanitizer's racecheck (which cannot see tcgen05.commit -> mbarrier ordering) can
                                      // verify the reuse of the activation ping-pong tiles

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             if (p.do_fwd) {
                 for (int l = 1; l <= L; ++l) {
                     const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
-                    const bool with_x = (l == 1);
+                    const bool with_x = (l == 1) && !p.x_from_global;     // folded pipeline input: staged by the epilogue warps
                     for (int kb0 = 0; kb0 < nkb; kb0 += p.kps, ++it) {
                         const int cnt = min(p.kps, nkb - kb0);
                         const int s = acquire(0);
@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             if (p.do_fwd) {
                 for (int l = 1; l <= L; ++l) {
                     const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
-                    run_gemm(nkb, false, l == 1, abuf0 + buf * abuf_bytes);
+                    // layer 1 reads X from its ring slots (TMA), or - folded pipeline input - from abuf 1 (staged by the epilogue warps)
+                    const bool x_glob = (l == 1) && p.x_from_global;
+                    run_gemm(nkb, false, l == 1 && !x_glob, abuf0 + (x_glob ? 1 : buf) * abuf_bytes);
                     if (l > 1) buf ^= 1;                     // layer l read buf, wrote buf^1
                     else buf = 0;                            // layer 1 wrote abuf 0
                 }
@@ -286,6 +288,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             __syncwarp();
             if (lane == 0) mbar_arrive(act_ready_bar);
         };
+        // ---------------- folded pipeline boundaries (see ChainParams): credit of the slots we will write, arrival of
+        // the tile we consume.  One thread spins (bounded), a named barrier among the 8 epilogue warps publishes the result.
+        uint32_t pp_epoch = 0u;
+        if (p.in_flag != nullptr || p.out_peer != nullptr) {
+            pp_epoch = *reinterpret_cast<const volatile uint32_t*>(p.pp_epoch);
+            if (threadIdx.x == 64) {
+                if (p.out_peer != nullptr) wait_flag_ge(p.out_credit, pp_epoch - 1u);
+                if (p.in_flag != nullptr) wait_flag_ge(p.in_flag, pp_epoch);
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        if (p.do_fwd && p.x_from_global) {
+            // stage the input tile [rows x in] (written into act[0] by the previous stage over NVLink) as layer 1's B operand
+            // in abuf 1, and its lo twin for the weight-gradient GEMM of layer 1
+            const int in0 = p.layers[0].in;
+            const uint32_t dstx = abuf0 + 1u * abuf_bytes;
+            const float* __restrict__ xin = p.act[0] + (int64_t)row0 * p.act_ld[0];
+            for (int n = c_lo; n < c_hi; ++n) {
+                float x = 0.f;
+                if (m < in0 && n < p.mb_rows) {
+                    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(x) : "l"(xin + (int64_t)n * p.act_ld[0] + m));
+                    if (SPLIT) p.act_lo[0][(int64_t)(row0 + n) * p.act_ld[0] + m] = tf32_lo(x);
+                }
+                st_tile(dstx, n, m, x);
+            }
+            publish();
+        }
         if (p.do_fwd) {
             for (int l = 1; l <= L; ++l) {
                 const ChainLayer& ly = p.layers[l - 1];
@@ -328,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             else if (m_ok && n < p.mb_rows) {
                                 gout[(int64_t)n * p.act_ld[l] + m] = x;
                                 if (SPLIT) p.act_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + m] = tf32_lo(x);
+                                if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[l] + m] = x;
                             }
                         }
                     }
@@ -338,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             if (c_lo + j < p.mb_rows) {
                                 gout[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
                                 if (SPLIT) p.act_lo[l][(int64_t)(row0 + c_lo + j) * p.act_ld[l] + m] = tf32_lo(keep[j]);
+                                if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
                             }
                     }
                     wbuf ^= 1;
@@ -443,6 +474,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 }
             }
         }
+        if (p.do_fwd && !p.do_bwd && p.out_peer != nullptr) {
+            // the stage's output tile is in the next stage's receive slot: one fence, then its arrival flag
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                __threadfence_system();
+                st_relaxed_sys(p.out_flag, pp_epoch);
+            }
+        }
         if (p.do_bwd && !(p.do_fwd && p.do_loss)) {
             // backward-only launch (pipeline stage): stage dZ_L = gout (.) relu'(act_L) into smem
             const ChainLayer& ly = p.layers[L - 1];
@@ -453,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             for (int n = c_lo; n < c_hi; ++n) {
                 float x = 0.f;
                 if (m_ok && n < p.mb_rows) {
-                    x = g[(int64_t)n * p.act_ld[L] + m];
+                    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(x) : "l"(g + (int64_t)n * p.act_ld[L] + m));   // may be peer-written
                     if (ly.relu && !(y[(int64_t)n * p.act_ld[L] + m] > 0.f)) x = 0.f;
                     g[(int64_t)n * p.act_ld[L] + m] = x;     // the wgrad GEMM reads the masked gradient
                     if (SPLIT) p.dz_lo[L][(int64_t)(row0 + n) * p.act_ld[L] + m] = tf32_lo(x);
@@ -508,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         else if (m_ok && n < p.mb_rows) {
                             gprev[(int64_t)n * p.act_ld[l - 1] + m] = x;
                             if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + n) * p.act_ld[l - 1] + m] = tf32_lo(x);
+                            if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[0] + m] = x;
                         }
                     }
                 }
@@ -521,9 +561,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         if (c_lo + j < p.mb_rows) {
                             gprev[(int64_t)(c_lo + j) * p.act_ld[l - 1] + m] = keep[j];
                             if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + c_lo + j) * p.act_ld[l - 1] + m] = tf32_lo(keep[j]);
+                            if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[0] + m] = keep[j];
                         }
                 }
                 signal_ready(l - 1);
+            }
+            if (p.out_peer != nullptr && !p.first_stage) {
+                // dz[0] is in the previous stage's receive slot: one fence, then its arrival flag
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    __threadfence_system();
+                    st_relaxed_sys(p.out_flag, pp_epoch);
+                }
             }
         }
         tc_fence_before();
