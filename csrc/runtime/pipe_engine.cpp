@@ -238,7 +238,7 @@ int PipeEngine::emit_record(int stream) {
 
 // One launch that walks micro-batches [mu_base, mu_base + n_mu) through the whole stage
 // (csrc/kernels/mlp_chain.cu).  Returns the op index.
-int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd) {
+int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd, const ChainFold* fold) {
     ChainParams cp{};
     cp.n_layers = L_;
     for (int l = 0; l < L_; ++l) {
@@ -262,6 +262,11 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
     cp.sync_debug = (getenv("SSB_RACECHECK") && atoi(getenv("SSB_RACECHECK")) > 0) ? 1 : 0;
+    if (fold != nullptr && pp_ctx_ != nullptr) {
+        cp.in_flag = fold->in_flag; cp.x_from_global = fold->x_from_global ? 1 : 0;
+        cp.out_peer = fold->out_peer; cp.out_flag = fold->out_flag; cp.out_credit = fold->out_credit;
+        cp.pp_epoch = pp_ctx_->epoch_ptr();
+    }
     cp.ready = (gate_on_ && do_bwd && do_fwd) ? gate_ready_ : nullptr;
     if (getenv("SSB_CHAIN_TIMELINE")) {
         if (!chain_dbg_) {
@@ -380,6 +385,10 @@ void PipeEngine::plan_per_mubatch() {
     // every micro-batch live in their own rows of the stage's buffers until the step ends, for every schedule.
     auto env_on = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) > 0 : dflt; };
     const bool ll_ok = cfg_.dp_mode == 2 && dp_ctx_ != nullptr && dp_ctx_->ll_enabled();
+    // Folded pipeline boundaries (peer transport + chain kernel): no push / wait kernels at all - the chain launch of a
+    // micro-batch waits for its input tile's arrival flag itself (while its weights already stream in) and stores its
+    // output tile into the neighbour's receive slot from the epilogue that produces it.
+    const bool fold_pp = chain_ok_ && pp_ctx_ != nullptr && env_on("SSB_PP_FOLD", true);
     const bool defer_wgrad = chain_ok_ && cfg_.training && (cfg_.dp_mode == 0 || ll_ok) && env_on("SSB_PP_DEFER_WGRAD", true);
     std::vector<bool> first_write(L_ + 1, true);
     std::vector<bool> sw_joined(streams_.size(), false);
@@ -410,6 +419,10 @@ void PipeEngine::plan_per_mubatch() {
     for (int i = 0; i < n;) {
         const int opc = std::get<0>(instrs[i]);
         // ------------------------------------------------ communication group
+        if (fold_pp && opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
+            ++i;                                            // sends and receives happen inside the chain launches
+            continue;
+        }
         if (pp_ctx_ && opc >= I_RECV_ACT && opc <= I_SEND_GRAD) {
             // ---- peer-memory transport: pushes first (one-sided: they never wait for the peer's schedule position,
             // only for the credit of the previous step), then the waits for what this group receives
@@ -522,7 +535,15 @@ void PipeEngine::plan_per_mubatch() {
                 }
                 if (chain_ok_) {
                     // whole stage forward (+ loss head on the last stage) of this micro-batch in one launch
-                    add_chain(s, mu, 1, true, last, false);
+                    ChainFold cf;
+                    if (fold_pp) {
+                        if (!first) { cf.in_flag = pp_ctx_->act_arrived(mu); cf.x_from_global = true; }
+                        if (!last) {
+                            cf.out_peer = pp_ctx_->next_act_in(mu); cf.out_flag = pp_ctx_->next_act_arrived(mu);
+                            cf.out_credit = pp_ctx_->act_credit();
+                        }
+                    }
+                    add_chain(s, mu, 1, true, last, false, fold_pp ? &cf : nullptr);
                     if (!cfg_.training && last) {
                         Op am;
                         am.kind = OP_ARGMAX; am.stream = s;
@@ -563,7 +584,15 @@ void PipeEngine::plan_per_mubatch() {
                 if (chain_ok_) {
                     // dZ_L (from the loss head at forward time, or received from the next stage) -> ReLU mask ->
                     // the whole dgrad chain in one launch; then one wave of weight-gradient GEMMs
-                    add_chain(s, mu, 1, false, false, true);
+                    ChainFold cb;
+                    if (fold_pp) {
+                        if (!last) cb.in_flag = pp_ctx_->dz_arrived(mu);
+                        if (!first) {
+                            cb.out_peer = pp_ctx_->prev_dz_in(mu); cb.out_flag = pp_ctx_->prev_dz_arrived(mu);
+                            cb.out_credit = pp_ctx_->dz_credit();
+                        }
+                    }
+                    add_chain(s, mu, 1, false, false, true, fold_pp ? &cb : nullptr);
                     const int ev_dz_all = emit_record(s);
                     for (int l = L_; l >= 1 && !defer_wgrad; --l) {
                         const LayerSpec& ls = cfg_.layers[l - 1];

@@ -188,7 +188,15 @@ private:
     std::vector<DpLLPlan> ll_plans_;
     bool chain_ok_ = false;
     unsigned long long* chain_dbg_ = nullptr;
-    int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd);
+    // pipeline boundaries folded into a chain launch (peer-memory transport), see ChainParams
+    struct ChainFold {
+        const uint32_t* in_flag = nullptr;
+        bool x_from_global = false;
+        float* out_peer = nullptr;
+        uint32_t* out_flag = nullptr;
+        const uint32_t* out_credit = nullptr;
+    };
+    int add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool do_loss, bool do_bwd, const ChainFold* fold = nullptr);
     DpContext* dp_ctx_ = nullptr;
     NvlsContext* nvls_ctx_ = nullptr;
     PpContext* pp_ctx_ = nullptr;
