@@ -46,6 +46,7 @@ struct GemmParams {
     // that owns the row (no smem staging, no TMA reduce-add) which also stores the lo twin of the NEW weights - the
     // arena-wide split kernel after the optimizer step disappears.  Same [out, ldw] geometry as W; nullptr = TMA reduce-add.
     float* W_lo;
+    int acc_split;      // 3xTF32: small cross terms in their own accumulator + rotating main accumulators (ptx.cuh); 0 = one accumulator
     // fp32-equivalent mode (3xTF32): both operands come with a `lo` twin (x - trunc_tf32(x)); FWD/DGRAD
     // also emit the lo twin of their output so the next GEMM can consume it
     int split;
@@ -195,6 +196,7 @@ struct DpLLPlan {
     DpLLEntry* entries_dev;
     int grid, smem_bytes;
 };
+int acc_split_default();   // tc_gemm.cu: SSB_ACC_SPLIT (default 1)
 int dp_ll_tiles(int in, int out);
 size_t dp_ll_zone_lines(int dp, int n_tiles);
 const char* dp_ll_plan(DpLLPlan* plan, const DpLLLayer* layers, int n_layers, int rows, const DpLLParams& base);
@@ -245,6 +247,8 @@ struct ChainParams {
     float* out_peer;
     uint32_t* out_flag;
     const uint32_t* out_credit;
+    int acc_split;                   // 3xTF32: small cross terms in their own accumulator + rotating main accumulators (ptx.cuh); 0 = one accumulator
+    int head_prefetch;               // loss head: fetch the targets before waiting for the logits
     int sync_debug;                  // SSB_RACECHECK=1: an explicit named barrier among the epilogue warps per layer, so that
                                      // compute-sanitizer's racecheck (which cannot see tcgen05.commit -> mbarrier ordering) can
                                      // verify the reuse of the activation ping-pong tiles

@@ -88,10 +88,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
     // 3xTF32: up to 4 rotating main accumulators (long reductions only: layer 1) + one for the small cross terms, see ptx.cuh
     constexpr int kTmemBudget = 512;
-    const int max_rot = SPLIT ? acc_rotation(1 << 20, N, kTmemBudget) : 1;
+    const bool acc_split = SPLIT && p.acc_split != 0;
+    const int max_rot = acc_split ? acc_rotation(1 << 20, N, kTmemBudget) : 1;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)N * (SPLIT ? (uint32_t)max_rot + 1u : 1u)) tmem_cols <<= 1;
-    const uint32_t small_off = SPLIT ? (uint32_t)N * (uint32_t)max_rot : 0u;
+    while (tmem_cols < (uint32_t)N * (acc_split ? (uint32_t)max_rot + 1u : 1u)) tmem_cols <<= 1;
+    const uint32_t small_off = acc_split ? (uint32_t)N * (uint32_t)max_rot : 0u;
     // loss-head transpose scratch [N][kScratchLd] floats, behind the barriers (128 B further)
     const uint32_t scratch_off = p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2) + 128u;
 
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     tc_fence_after();
                 }
                 if (lane == 0) DBG(1, 3 * gemm_i);
-                const int rot = SPLIT ? acc_rotation(nkb, N, kTmemBudget) : 1;
+                const int rot = acc_split ? acc_rotation(nkb, N, kTmemBudget) : 1;
                 for (int kb0 = 0; kb0 < nkb; kb0 += p.kps, ++it) {
                     const int cnt = min(p.kps, nkb - kb0);
                     const int s = it % p.stages;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                               (kb | k4) != 0 ? 1u : 0u);
                                     umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
                                     umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
-                                              (kb >= rot || k4 != 0) ? 1u : 0u);
+                                              (!acc_split || kb >= rot || k4 != 0) ? 1u : 0u);   // one accumulator: the cross terms are in it already
                                 }
                             } else
 #pragma unroll
@@ -321,11 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 const bool m_ok = m < ly.out;
                 const float bias = m_ok ? __ldg(p.W + ly.w_off + (int64_t)m * ly.ldw + ly.in) : 0.f;
                 const bool is_logits = (l == L) && p.do_loss;
-                const int rot_f = SPLIT ? acc_rotation((ly.in + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;   // as the MMA warp chose
+                const int rot_f = acc_split ? acc_rotation((ly.in + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;   // as the MMA warp chose
                 // loss head: the targets do not depend on the MMA - fetch this lane's row before waiting for the logits
                 // (the head is ONE warp on the critical path between the last forward and the first backward GEMM)
                 float tg_pre[16];
-                const bool head_pre = is_logits && q == 0 && half == 0 && ly.out <= 16;
+                const bool head_pre = p.head_prefetch && is_logits && q == 0 && half == 0 && ly.out <= 16;
                 if (head_pre) {
                     const float* __restrict__ tgp = p.target + (int64_t)(row0 + lane) * p.ldt;
 #pragma unroll
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 float ssum = 0.f;
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    tgv[k] = (n == lane) ? tg_pre[k] : ((k < C && row_ok) ? __ldg(tg + k) : 0.f);
+                                    tgv[k] = (head_pre && n == lane) ? tg_pre[k] : ((k < C && row_ok) ? __ldg(tg + k) : 0.f);
                                     ev[k] = (k < C) ? expf(zr[k] - gmax) : 0.f;
                                     ssum += ev[k];
                                 }
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             for (int l = L; l >= bwd_lo; --l) {
                 const ChainLayer& ly = p.layers[l - 1];
                 const bool m_ok = m < ly.in;                 // output feature of dgrad = input feature of layer l
-                const int rot_b = SPLIT ? acc_rotation((ly.out + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;
+                const int rot_b = acc_split ? acc_rotation((ly.out + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;
                 const bool mask_on = (l >= 2) && p.layers[l - 2].relu;
                 const float* __restrict__ yprev = p.act[l - 1] + (int64_t)row0 * p.act_ld[l - 1];
                 float* __restrict__ gprev = p.dz[l - 1] + (int64_t)row0 * p.act_ld[l - 1];

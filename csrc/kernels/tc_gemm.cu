@@ -76,10 +76,11 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
 
     // 3xTF32 accumulators (ptx.cuh): one for the small cross terms; FWD / DGRAD reductions over >= 8 k-blocks rotate the
     // hi*hi products over up to 4 main accumulators, inside half of the TMEM columns.
-    const int rot = (p.split && MODE != GEMM_WGRAD) ? acc_rotation(num_kb, p.block_n, 256) : 1;   // 256 of 512 columns: two CTAs of this kernel may share an SM
+    const bool acc_split = p.split && p.acc_split;
+    const int rot = (acc_split && MODE != GEMM_WGRAD) ? acc_rotation(num_kb, p.block_n, 256) : 1;   // 256 of 512 columns: two CTAs of this kernel may share an SM
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)p.block_n * (p.split ? (uint32_t)rot + 1u : 1u)) tmem_cols <<= 1;
-    const uint32_t small_off = p.split ? (uint32_t)p.block_n * (uint32_t)rot : 0u;
+    while (tmem_cols < (uint32_t)p.block_n * (acc_split ? (uint32_t)rot + 1u : 1u)) tmem_cols <<= 1;
+    const uint32_t small_off = acc_split ? (uint32_t)p.block_n * (uint32_t)rot : 0u;
 
     const bool db_active = (MODE == GEMM_WGRAD) && (p.db != nullptr) && (by == 0);
 
@@ -175,7 +176,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                             umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
                                       idesc, 1u);
                             umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
-                                      idesc, (kb >= rot || k4 != 0) ? 1u : 0u);
+                                      idesc, (!acc_split || kb >= rot || k4 != 0) ? 1u : 0u);
                         }
                     } else
 #pragma unroll
@@ -433,6 +434,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_group_kernel(const GemmG
 }
 
 // =========================================================================== host side
+// SSB_ACC_SPLIT=0: all three 3xTF32 products into one accumulator (the round-1 behaviour), for A/B measurements
+int acc_split_default() {
+    static const int v = [] { const char* e = getenv("SSB_ACC_SPLIT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    return v;
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -510,7 +516,7 @@ const char* gemm_plan_fwd(GemmPlan* plan, const float* W, int ldw, const float* 
     plan->tmC = plan->tmA;
     plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
     if (lo.A != nullptr && lo.B != nullptr) {
-        p.split = 1; p.out_lo = lo.out;
+        p.split = 1; p.out_lo = lo.out; p.acc_split = acc_split_default();
         if (const char* e = make_tmap(&plan->tmAlo, lo.A, in, out, ldw, kBlockM)) return e;
         if (const char* e = make_tmap(&plan->tmBlo, lo.B, in, rows, ldx, p.block_n)) return e;
     }
@@ -531,7 +537,7 @@ const char* gemm_plan_dgrad(GemmPlan* plan, const float* W, int ldw, const float
     plan->tmC = plan->tmA;
     plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
     if (lo.A != nullptr && lo.B != nullptr) {
-        p.split = 1; p.out_lo = lo.out;
+        p.split = 1; p.out_lo = lo.out; p.acc_split = acc_split_default();
         if (const char* e = make_tmap(&plan->tmAlo, lo.A, in, out, ldw, 32, true)) return e;
         if (const char* e = make_tmap(&plan->tmBlo, lo.B, out, rows, lddz, p.block_n)) return e;
     }
@@ -557,7 +563,7 @@ const char* gemm_plan_wgrad(GemmPlan* plan, const float* dZ, int lddz, const flo
     if (const char* e = make_tmap(&plan->tmB, X, in, rows, ldx, 32, true)) return e;
     plan->tmAlo = plan->tmA; plan->tmBlo = plan->tmB;
     if (lo.A != nullptr && lo.B != nullptr) {
-        p.split = 1;
+        p.split = 1; p.acc_split = acc_split_default();
         if (const char* e = make_tmap(&plan->tmAlo, lo.A, out, rows, lddz, 32, true)) return e;
         if (const char* e = make_tmap(&plan->tmBlo, lo.B, in, rows, ldx, 32, true)) return e;
     }

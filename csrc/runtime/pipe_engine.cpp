@@ -262,6 +262,8 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
     cp.sync_debug = (getenv("SSB_RACECHECK") && atoi(getenv("SSB_RACECHECK")) > 0) ? 1 : 0;
+    cp.acc_split = acc_split_default();
+    cp.head_prefetch = (getenv("SSB_HEAD_PREFETCH") && atoi(getenv("SSB_HEAD_PREFETCH")) == 0) ? 0 : 1;
     if (fold != nullptr && pp_ctx_ != nullptr) {
         cp.in_flag = fold->in_flag; cp.x_from_global = fold->x_from_global ? 1 : 0;
         cp.out_peer = fold->out_peer; cp.out_flag = fold->out_flag; cp.out_credit = fold->out_credit;
@@ -868,6 +870,7 @@ void PipeEngine::build_coalesced() {
     }
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
+    const bool wgrad_rmw = !(getenv("SSB_WGRAD_RMW") && atoi(getenv("SSB_WGRAD_RMW")) == 0);   // A/B: TMA reduce-add + split kernel
     // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
     // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
     // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
@@ -949,7 +952,7 @@ void PipeEngine::build_coalesced() {
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
         // narrow stages (latency-bound): the update kernel read-modify-writes its tile and refreshes the lo twins itself;
         // wide layers (bandwidth-bound) keep the TMA reduce-add + the arena-wide split kernel
-        if (fuse && cfg_.split && chain) g.p.W_lo = W_lo_ + ls.offset;
+        if (fuse && cfg_.split && chain && wgrad_rmw) g.p.W_lo = W_lo_ + ls.offset;
         if (group_wgrad) {                                  // launched together after the loop
             grouped.push_back(g);
             continue;
@@ -1016,7 +1019,7 @@ void PipeEngine::build_coalesced() {
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
     // lo twins of the updated weights: written by the update kernels themselves (SGD-fused wgrad, LL data-parallel kernel);
     // every other update path (NCCL / NVLS / flag-protocol kernels) is followed by the arena-wide split kernel
-    const bool wlo_in_update = (fuse && cfg_.split && chain) || !ll_layers.empty();
+    const bool wlo_in_update = (fuse && cfg_.split && chain && wgrad_rmw) || !ll_layers.empty();
     if (w_lo_needed_ && !wlo_in_update) {
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
