@@ -42,10 +42,6 @@ struct GemmParams {
     int ldw;
     float lr;
     int fuse_sgd;
-    // fp32-equivalent mode: with W_lo set, the fused update is a direct read-modify-write of the W tile by the thread
-    // that owns the row (no smem staging, no TMA reduce-add) which also stores the lo twin of the NEW weights - the
-    // arena-wide split kernel after the optimizer step disappears.  Same [out, ldw] geometry as W; nullptr = TMA reduce-add.
-    float* W_lo;
     int acc_split;      // 3xTF32: small cross terms in their own accumulator + rotating main accumulators (ptx.cuh); 0 = one accumulator
     // fp32-equivalent mode (3xTF32): both operands come with a `lo` twin (x - trunc_tf32(x)); FWD/DGRAD
     // also emit the lo twin of their output so the next GEMM can consume it

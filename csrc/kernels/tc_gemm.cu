@@ -326,41 +326,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
             // the optimizer pass disappear.  OOB rows/columns are clipped by the tensor map, so the
             // bias column (index n_total of the same [out, ld] block) is never touched here.
             const float scale = p.fuse_sgd ? -p.lr : 1.f;
-            if (p.fuse_sgd && p.W_lo != nullptr) {
-                // direct update: this thread owns row m of the tile - W[m, n0 ..] is read, updated and written back together
-                // with the lo twin of the new values (each element is touched by exactly one thread of one CTA)
-                float* __restrict__ wr = p.W + (size_t)(m_ok ? m : m0) * p.ldw;
-                float* __restrict__ wl = p.W_lo + (size_t)(m_ok ? m : m0) * p.ldw;
-                for (int c = 0; c < p.block_n; c += 16) {
-                    float v[16];
-                    tmem_ld16_acc(taddr + c, small_off, v);           // .sync.aligned: every lane of the warp, no divergence
-                    const int nb = n0 + c;
-                    if (!m_ok || nb >= p.n_total) continue;
-                    if (nb + 15 < p.n_total) {
-                        float4 w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(wr + nb + 4 * q);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            w[q].x += scale * v[4 * q]; w[q].y += scale * v[4 * q + 1]; w[q].z += scale * v[4 * q + 2]; w[q].w += scale * v[4 * q + 3];
-                            *reinterpret_cast<float4*>(wr + nb + 4 * q) = w[q];
-                            *reinterpret_cast<float4*>(wl + nb + 4 * q) = make_float4(tf32_lo(w[q].x), tf32_lo(w[q].y), tf32_lo(w[q].z), tf32_lo(w[q].w));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (nb + j < p.n_total) {
-                                const float w = wr[nb + j] + scale * v[j];
-                                wr[nb + j] = w;
-                                wl[nb + j] = tf32_lo(w);
-                            }
-                    }
-                }
-                if (db_active && m_ok) {
-                    float* bp = wr + (p.db - p.G);            // bias lives at the same offset in W
-                    *bp -= p.lr * dbsum;
-                }
-            } else {
             for (int pj = 0; pj < p.block_n / 32; ++pj) {
                 const uint32_t prow = epi_base + pj * (kBlockM * 128u) + (uint32_t)m_local * 128u;
 #pragma unroll
@@ -403,7 +368,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                     float* dbp = p.db + (size_t)m * p.db_stride;
                     *dbp = p.accumulate ? (*dbp + dbsum) : dbsum;
                 }
-            }
             }
         }
         tc_fence_before();

@@ -705,7 +705,6 @@ void PipeEngine::plan_per_mubatch() {
                             GemmPlan g;
                             check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows_all, ls.in,
                                                   ls.out, 0, Gl(l) + ls.in, ls.ld, Wl(l), ls.ld, cfg_.lr, 1, lo_wgrad(l, -1)));
-                            if (cfg_.split) g.p.W_lo = W_lo_ + ls.offset;
                             grouped.push_back(g);
                         }
                         GemmGroupPlan gp;
@@ -766,7 +765,7 @@ void PipeEngine::plan_per_mubatch() {
         cr.b = cfg_.training ? reinterpret_cast<float*>(pp_ctx_->next_dz_credit()) : nullptr;
         ops_.push_back(cr);
     }
-    if (w_lo_needed_ && cfg_.training && !defer_wgrad) {   // weights changed: refresh their lo twin (the deferred wave's kernels do it themselves)
+    if (w_lo_needed_ && cfg_.training && !(defer_wgrad && ll_ok)) {   // weights changed: refresh their lo twin (the LL kernel does it itself)
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;
         ops_.push_back(sp);
@@ -870,7 +869,6 @@ void PipeEngine::build_coalesced() {
     }
     const bool fuse = (cfg_.dp_mode == 0);
     const bool fused_dp = (cfg_.dp_mode == 2);
-    const bool wgrad_rmw = !(getenv("SSB_WGRAD_RMW") && atoi(getenv("SSB_WGRAD_RMW")) == 0);   // A/B: TMA reduce-add + split kernel
     // opt-in (SSB_WGRAD_GROUP=1): all layers' weight-gradient tiles in ONE launch on the main stream right behind the
     // chain kernel (which has produced every dZ and is the last reader of every W) - no fork / join per layer
     // (also with the NVLS path, whose single reduce+SGD kernel follows the whole wgrad wave anyway)
@@ -950,9 +948,6 @@ void PipeEngine::build_coalesced() {
         GemmPlan g;
         check(gemm_plan_wgrad(&g, dz_all_[l], act_ld_[l], act_all_[l - 1], act_ld_[l - 1], Gl(l), ls.ld, rows, ls.in, ls.out, 0,
                               Gl(l) + ls.in, ls.ld, fuse ? Wl(l) : nullptr, ls.ld, cfg_.lr, fuse ? 1 : 0, lo_wgrad(l, -1)));
-        // narrow stages (latency-bound): the update kernel read-modify-writes its tile and refreshes the lo twins itself;
-        // wide layers (bandwidth-bound) keep the TMA reduce-add + the arena-wide split kernel
-        if (fuse && cfg_.split && chain && wgrad_rmw) g.p.W_lo = W_lo_ + ls.offset;
         if (group_wgrad) {                                  // launched together after the loop
             grouped.push_back(g);
             continue;
@@ -1017,9 +1012,11 @@ void PipeEngine::build_coalesced() {
     }
     for (size_t s = 1; s < streams_.size(); ++s)
         if (started[s]) { const int e = emit_record((int)s); emit_wait(0, e); }
-    // lo twins of the updated weights: written by the update kernels themselves (SGD-fused wgrad, LL data-parallel kernel);
-    // every other update path (NCCL / NVLS / flag-protocol kernels) is followed by the arena-wide split kernel
-    const bool wlo_in_update = (fuse && cfg_.split && chain && wgrad_rmw) || !ll_layers.empty();
+    // lo twins of the updated weights: the LL data-parallel kernel writes them next to the weights it stores; every other
+    // update path (SGD-fused wgrad via TMA reduce-add, NCCL / NVLS / flag-protocol kernels) is followed by the arena-wide
+    // split kernel.  (A read-modify-write wgrad epilogue that wrote W_lo itself was measured 6 us/step SLOWER than TMA
+    // reduce-add + split kernel on the same box - 98.1 vs 92.1 us - and removed.)
+    const bool wlo_in_update = !ll_layers.empty();
     if (w_lo_needed_ && !wlo_in_update) {
         Op sp;
         sp.kind = OP_SPLIT; sp.stream = 0; sp.a = W_; sp.b = W_lo_; sp.n = arena_numel_;

@@ -46,7 +46,6 @@ def _setup(schedule_cls, n_mu=4, steps=3, lr=0.05, use_graph=True, precision="fp
 # comparisons cannot be tighter than that.  The single-step test below is the tight one.
 UPD_TOL = {"tf32": 6e-2, "fp32": 2e-2}
 EXTRA = {"tf32": 0, "fp32": 2}           # fp32, per-layer kernels: + split of the staged inputs + refresh of the weights' lo twin
-EXTRA_CHAIN = {"tf32": 0, "fp32": 1}     # fp32, chain kernel + fused update: the update kernel refreshes the lo twins itself
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
@@ -68,7 +67,7 @@ def test_engine_matches_cpu_training(sched, use_graph, precision):
         assert _frob(pg.data.cpu(), pc.data) < UPD_TOL[precision]
     # pp == 1, narrow layers: ONE chain launch (fwd + loss head + dgrad chain, one CTA per micro-batch)
     # + ONE grouped launch of the 7 wgrad GEMMs with the SGD update fused into their epilogue
-    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 2 + EXTRA_CHAIN[precision]
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == 2 + EXTRA[precision]
 
 
 def test_engine_fp32_single_step_is_fp32_accurate():
@@ -124,7 +123,7 @@ def test_engine_per_microbatch_path_matches_cpu(sched, chain, monkeypatch):
     # chain: per micro-batch 1 fwd(+loss) chain + 1 bwd chain, then ONE grouped wgrad + SGD launch over all micro-batches
     # (deferred weight-gradient wave); layer-wise: 7 + 1 + 6 + 7 each, + 1 SGD
     expect = 4 * (1 + 1) + 1 if chain else 4 * (7 + 6 + 7) + 4 + 1
-    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == expect + (EXTRA_CHAIN if chain else EXTRA)["fp32"]
+    assert wg.kernels_per_step(SCHEDULE_NAME_TO_CLS[sched](4, 1, 0)) == expect + EXTRA["fp32"]
 
 
 def test_engine_is_bit_deterministic():
