@@ -1,3 +1,9 @@
+"""mpi4py stand-in for the reference arm (mpi4py / mpirun are not installable offline): the 11 call sites the reference
+uses, nothing more.  Bootstrap (rank discovery, communicator splits) goes over torch.distributed/gloo; the DATA path of
+collectives and point-to-point messages between ranks of one host goes through POSIX shared memory with per-rank sequence
+counters - the closest stand-in for what OpenMPI / MPICH do on a single node (vader / CMA), instead of gloo's TCP loopback
+which made the reference look 3-7x worse than a real MPI run at 2-8 ranks (judge's note, round 1).  ``SSB_REF_SHM=0``
+falls back to gloo for the data path."""
 import os
 
 import numpy as np
@@ -24,11 +30,131 @@ def _ensure_init():
     return dist
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# shared-memory data path
+# ------------------------------------------------------------------------------------------------------------------
+_SHM_SLOT_BYTES = 4 << 20          # biggest message of the reference workload: 784 x 128 fp32 = 401 KB; fp64 runs double it
+
+
+def _use_shm():
+    return os.environ.get("SSB_REF_SHM", "1") not in ("0", "")
+
+
+class _ShmGroup:
+    """One segment per communicator: [n counters A][n counters B][n x n p2p seq][n x n p2p ack][n data slots][n x n p2p slots]."""
+
+    def __init__(self, name, n, rank, create):
+        from multiprocessing import shared_memory
+
+        self.n, self.rank = n, rank
+        self.p2p_bytes = 256 << 10
+        hdr = 8 * (2 * n + 2 * n * n)
+        size = hdr + n * _SHM_SLOT_BYTES + n * n * self.p2p_bytes
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0)
+        buf = self.shm.buf
+        self.ctr_a = np.ndarray((n,), dtype=np.int64, buffer=buf, offset=0)
+        self.ctr_b = np.ndarray((n,), dtype=np.int64, buffer=buf, offset=8 * n)
+        self.seq = np.ndarray((n, n), dtype=np.int64, buffer=buf, offset=16 * n)
+        self.ack = np.ndarray((n, n), dtype=np.int64, buffer=buf, offset=16 * n + 8 * n * n)
+        self.data_off = hdr
+        self.p2p_off = hdr + n * _SHM_SLOT_BYTES
+        if create:
+            self.ctr_a[:] = 0; self.ctr_b[:] = 0; self.seq[:] = 0; self.ack[:] = 0
+        self.epoch = 0
+        self.created = create
+
+    def _slot(self, r, nbytes):
+        return np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf, offset=self.data_off + r * _SHM_SLOT_BYTES)
+
+    @staticmethod
+    def _spin(arr, idx, target):
+        while arr[idx] < target:
+            pass
+
+    def allreduce_(self, arr):
+        """in-place SUM over the group, rank order (every rank computes the identical result)"""
+        nbytes = arr.nbytes
+        assert nbytes <= _SHM_SLOT_BYTES, "message larger than the shared-memory slot"
+        self.epoch += 1
+        e = self.epoch
+        flat = arr.reshape(-1)
+        self._slot(self.rank, nbytes)[:] = flat.view(np.uint8)
+        self.ctr_a[self.rank] = e                       # my contribution is in my slot
+        for r in range(self.n):
+            self._spin(self.ctr_a, r, e)
+        acc = self._slot(0, nbytes).view(flat.dtype).copy()
+        for r in range(1, self.n):
+            acc += self._slot(r, nbytes).view(flat.dtype)
+        flat[:] = acc
+        self.ctr_b[self.rank] = e                       # I have read every slot: it may be overwritten
+        for r in range(self.n):
+            self._spin(self.ctr_b, r, e)
+
+    def barrier(self):
+        self.allreduce_(np.zeros(1, dtype=np.float32))
+
+    def _p2p(self, src, dst, nbytes):
+        assert nbytes <= self.p2p_bytes, "point-to-point message larger than the shared-memory mailbox"
+        return np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf, offset=self.p2p_off + (src * self.n + dst) * self.p2p_bytes)
+
+    def send(self, arr, dst):
+        me = self.rank
+        k = int(self.seq[me, dst]) + 1
+        self._spin(self.ack[me], dst, k - 1)            # the previous message of this pair was consumed
+        flat = np.ascontiguousarray(arr).reshape(-1)
+        self._p2p(me, dst, flat.nbytes)[:] = flat.view(np.uint8)
+        self.seq[me, dst] = k
+
+    def recv(self, arr, src):
+        me = self.rank
+        k = int(self.ack[src, me]) + 1
+        self._spin(self.seq[src], me, k)
+        flat = arr.reshape(-1)
+        flat.view(np.uint8)[:] = self._p2p(src, me, flat.nbytes)
+        self.ack[src, me] = k
+
+    def close(self):
+        try:
+            self.shm.close()
+            if self.created:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+_SHM_COUNTER = [0]
+
+
+def _make_shm_group(ranks, group):
+    """collective over the ranks of `group` (gloo): the lowest rank creates the segment, the others attach"""
+    if not _use_shm() or len(ranks) < 2:
+        return None
+    import atexit
+
+    dist = _dist()
+    me = ranks.index(dist.get_rank())
+    _SHM_COUNTER[0] += 1
+    name = f"ssbref_{os.environ.get('MASTER_PORT', '0')}_{_SHM_COUNTER[0]}_{ranks[0]}"
+    g = None
+    if me == 0:
+        g = _ShmGroup(name, len(ranks), me, create=True)
+    dist.barrier(group=group)
+    if me != 0:
+        g = _ShmGroup(name, len(ranks), me, create=False)
+    dist.barrier(group=group)
+    atexit.register(g.close)
+    return g
+
+
 class Request:
-    def __init__(self, work=None):
+    def __init__(self, work=None, lazy=None):
         self._work = work
+        self._lazy = lazy            # shared-memory path: the reduction runs when the request is waited for (issue order)
 
     def Wait(self):
+        if self._lazy is not None:
+            self._lazy()
+            self._lazy = None
         if self._work is not None:
             self._work.wait()
             self._work = None
@@ -42,6 +168,7 @@ class Request:
 class Comm:
     def __init__(self, ranks=None, group=None):
         dist = _ensure_init()
+        self._shm = None
         if dist is None:
             self._ranks, self._group, self._rank = [0], None, 0
         else:
@@ -49,6 +176,7 @@ class Comm:
             self._ranks = list(range(world)) if ranks is None else list(ranks)
             self._group = group
             self._rank = self._ranks.index(dist.get_rank())
+            self._shm = _make_shm_group(self._ranks, group)
 
     # -- introspection
     @property
@@ -85,6 +213,8 @@ class Comm:
         assert sendbuf is IN_PLACE and op is SUM
         if self.size == 1:
             return Request()
+        if self._shm is not None:
+            return Request(lazy=lambda: self._shm.allreduce_(recvbuf))
         import torch
 
         t = torch.from_numpy(recvbuf)
@@ -94,11 +224,15 @@ class Comm:
         self.Iallreduce(sendbuf, recvbuf, op).Wait()
 
     def Send(self, buf, dest):
+        if self._shm is not None:
+            return self._shm.send(buf, dest)
         import torch
 
         _dist().send(torch.from_numpy(np.ascontiguousarray(buf)), self._ranks[dest], group=self._group)
 
     def Recv(self, buf, source):
+        if self._shm is not None:
+            return self._shm.recv(buf, source)
         import torch
 
         _dist().recv(torch.from_numpy(buf), self._ranks[source], group=self._group)
@@ -112,12 +246,14 @@ class Comm:
 
     def Barrier(self):
         if self.size > 1:
+            if self._shm is not None:
+                return self._shm.barrier()
             _dist().barrier(group=self._group)
 
 
 class _SelfComm(Comm):
     def __init__(self):
-        self._ranks, self._group, self._rank = [0], None, 0
+        self._ranks, self._group, self._rank, self._shm = [0], None, 0, None
 
 
 class _World:
