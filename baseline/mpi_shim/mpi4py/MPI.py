@@ -33,7 +33,7 @@ def _ensure_init():
 # ------------------------------------------------------------------------------------------------------------------
 # shared-memory data path
 # ------------------------------------------------------------------------------------------------------------------
-_SHM_SLOT_BYTES = 4 << 20          # biggest message of the reference workload: 784 x 128 fp32 = 401 KB; fp64 runs double it
+_SHM_SLOT_BYTES = 1 << 20          # biggest message of the reference workload: 784 x 128 fp32 = 401 KB; fp64 runs double it
 
 
 def _use_shm():
@@ -47,7 +47,7 @@ class _ShmGroup:
         from multiprocessing import shared_memory
 
         self.n, self.rank = n, rank
-        self.p2p_bytes = 256 << 10
+        self.p2p_bytes = 160 << 10      # biggest boundary tile: validation pass, 128 rows x 127 features (x 8 bytes in fp64 runs)
         hdr = 8 * (2 * n + 2 * n * n)
         size = hdr + n * _SHM_SLOT_BYTES + n * n * self.p2p_bytes
         self.shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0)
@@ -136,9 +136,20 @@ def _make_shm_group(ranks, group):
     _SHM_COUNTER[0] += 1
     name = f"ssbref_{os.environ.get('MASTER_PORT', '0')}_{_SHM_COUNTER[0]}_{ranks[0]}"
     g = None
+    ok = [True]
     if me == 0:
-        g = _ShmGroup(name, len(ranks), me, create=True)
-    dist.barrier(group=group)
+        try:
+            n = len(ranks)
+            need = 8 * (2 * n + 2 * n * n) + n * _SHM_SLOT_BYTES + n * n * (160 << 10)
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize < 2 * need:          # a tmpfs that is too small ends in SIGBUS, not in an exception
+                raise OSError("not enough space in /dev/shm")
+            g = _ShmGroup(name, n, me, create=True)
+        except Exception:
+            ok[0] = False
+    dist.broadcast_object_list(ok, src=ranks[0], group=group)     # everyone takes the leader's decision
+    if not ok[0]:
+        return None                                               # gloo data path for this communicator
     if me != 0:
         g = _ShmGroup(name, len(ranks), me, create=False)
     dist.barrier(group=group)
@@ -213,7 +224,7 @@ class Comm:
         assert sendbuf is IN_PLACE and op is SUM
         if self.size == 1:
             return Request()
-        if self._shm is not None:
+        if self._shm is not None and recvbuf.nbytes <= _SHM_SLOT_BYTES:
             return Request(lazy=lambda: self._shm.allreduce_(recvbuf))
         import torch
 
@@ -224,14 +235,14 @@ class Comm:
         self.Iallreduce(sendbuf, recvbuf, op).Wait()
 
     def Send(self, buf, dest):
-        if self._shm is not None:
+        if self._shm is not None and buf.nbytes <= self._shm.p2p_bytes:
             return self._shm.send(buf, dest)
         import torch
 
         _dist().send(torch.from_numpy(np.ascontiguousarray(buf)), self._ranks[dest], group=self._group)
 
     def Recv(self, buf, source):
-        if self._shm is not None:
+        if self._shm is not None and buf.nbytes <= self._shm.p2p_bytes:
             return self._shm.recv(buf, source)
         import torch
 
