@@ -59,7 +59,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 // (Round 2 also tried deriving the lo twins of the streamed weight tiles in shared memory instead of loading them - half
 // the L2->SM bytes, bit-identical results - but with only 3 ring slots of 40 KB the extra split stage in the slot cycle
 // cost more than the bytes saved: 92.8 vs 78.7 us/step.  Removed; see profiles/variants_r2.md.)
-template <bool SPLIT>
+// FOLD (pipeline boundaries inside the kernel, see ChainParams) is a compile-time switch as well: merely carrying that code
+// - a prologue, two predicated peer stores per element in the epilogues - cost the single-GPU / data-parallel step 8 us
+// (same-box bisect, profiles/variants_r2.md), so launches without a folded boundary use the instantiation without it.
+template <bool SPLIT, bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             if (p.do_fwd) {
                 for (int l = 1; l <= L; ++l) {
                     const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
-                    const bool with_x = (l == 1) && !p.x_from_global;     // folded pipeline input: staged by the epilogue warps
+                    const bool with_x = (l == 1) && !(FOLD && p.x_from_global);   // folded pipeline input: staged by the epilogue warps
                     for (int kb0 = 0; kb0 < nkb; kb0 += p.kps, ++it) {
                         const int cnt = min(p.kps, nkb - kb0);
                         const int s = acquire(0);
@@ -196,7 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     tc_fence_after();
                 }
                 if (lane == 0) DBG(1, 3 * gemm_i);
-                const int rot = acc_split ? acc_rotation(nkb, N, kTmemBudget) : 1;
+                // only LONG reductions (layer 1 of the first stage: K = 784) use the extra accumulators; the 128-wide layers
+                // keep one accumulator and the lean epilogue (their error is ~4x cuBLAS fp32 already)
+                const bool acc_l = acc_split && nkb >= 8;
+                const int rot = acc_l ? acc_rotation(nkb, N, kTmemBudget) : 1;
+                uint32_t rot_i = 0u;                          // main accumulator of the current k-block (round robin)
                 for (int kb0 = 0; kb0 < nkb; kb0 += p.kps, ++it) {
                     const int cnt = min(p.kps, nkb - kb0);
                     const int s = it % p.stages;
@@ -205,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     if (kb0 + cnt >= nkb && lane == 0) DBG(1, 3 * gemm_i + 1);
                     const uint32_t a_src = smem_base + s * stage_bytes;
                     if (elect_one()) {
+                        uint32_t rot_e = rot_i;               // the elected lane's running copy; every lane advances rot_i below
                         for (int j = 0; j < cnt; ++j) {
                             const uint32_t a_j = a_src + j * kABytes;
                             const uint32_t b_j = b_from_stage ? a_src + stage_b_off + j * b_bytes : bsrc + (kb0 + j) * b_bytes;
@@ -215,15 +223,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             if (SPLIT) {                           // lo*hi + hi*lo + hi*hi (raw tiles are the hi parts)
                                 const uint32_t al_lo = a_lo + (half_stage >> 4);
                                 const uint32_t bl_lo = b_lo + ((b_from_stage ? half_stage : lo_off) >> 4);
+                                if (!acc_l) {
+                                    // short reduction: one accumulator, nothing but the three MMAs in the issue path (this warp sits
+                                    // on the ring's critical cycle: every extra instruction per k-block shows up 73 times per step)
 #pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    const int kb = kb0 + j;
-                                    const uint32_t main_acc = tmem_base + (uint32_t)(kb % rot) * (uint32_t)N;   // rotate the hi*hi chains
-                                    umma_tf32(tmem_base + small_off, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
-                                              (kb | k4) != 0 ? 1u : 0u);
-                                    umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
-                                    umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
-                                              (!acc_split || kb >= rot || k4 != 0) ? 1u : 0u);   // one accumulator: the cross terms are in it already
+                                    for (int k4 = 0; k4 < 4; ++k4) {
+                                        umma_tf32(tmem_base, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                                  ((kb0 + j) | k4) != 0 ? 1u : 0u);
+                                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
+                                        umma_tf32(tmem_base, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id, 1u);
+                                    }
+                                } else {
+                                    // long reduction: small cross terms in their own accumulator, hi*hi rotating over `rot` accumulators
+                                    const bool first_kb = (kb0 + j) == 0;
+                                    const uint32_t small_acc = tmem_base + small_off;
+                                    const uint32_t main_acc = tmem_base + rot_e * (uint32_t)N;
+                                    const bool main_fresh = (kb0 + j) < rot;   // first product into this main accumulator
+                                    rot_e = (rot_e + 1u == (uint32_t)rot) ? 0u : rot_e + 1u;
+#pragma unroll
+                                    for (int k4 = 0; k4 < 4; ++k4) {
+                                        umma_tf32(small_acc, umma_desc_pack(al_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                                  (first_kb && k4 == 0) ? 0u : 1u);
+                                        umma_tf32(small_acc, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(bl_lo + k4 * 2u, k_hi), id, 1u);
+                                        umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, ah), umma_desc_pack(b_lo + k4 * 2u, k_hi), id,
+                                                  (main_fresh && k4 == 0) ? 0u : 1u);
+                                    }
                                 }
                             } else
 #pragma unroll
@@ -234,6 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         umma_commit(empty_bar(s));
                         if (kb0 + cnt >= nkb) umma_commit(tmem_full_bar);
                     }
+                    if (acc_l)
+                        for (int j = 0; j < cnt; ++j) rot_i = (rot_i + 1u == (uint32_t)rot) ? 0u : rot_i + 1u;   // all lanes, off the issue path
                     __syncwarp();
                 }
                 if (lane == 0) DBG(1, 3 * gemm_i + 2);
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 for (int l = 1; l <= L; ++l) {
                     const int nkb = (p.layers[l - 1].in + (int)kBlockK - 1) / (int)kBlockK;
                     // layer 1 reads X from its ring slots (TMA), or - folded pipeline input - from abuf 1 (staged by the epilogue warps)
-                    const bool x_glob = (l == 1) && p.x_from_global;
+                    const bool x_glob = FOLD && (l == 1) && p.x_from_global;
                     run_gemm(nkb, false, l == 1 && !x_glob, abuf0 + (x_glob ? 1 : buf) * abuf_bytes);
                     if (l > 1) buf ^= 1;                     // layer l read buf, wrote buf^1
                     else buf = 0;                            // layer 1 wrote abuf 0
@@ -292,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         // ---------------- folded pipeline boundaries (see ChainParams): credit of the slots we will write, arrival of
         // the tile we consume.  One thread spins (bounded), a named barrier among the 8 epilogue warps publishes the result.
         uint32_t pp_epoch = 0u;
+        if constexpr (FOLD) {
         if (p.in_flag != nullptr || p.out_peer != nullptr) {
             pp_epoch = *reinterpret_cast<const volatile uint32_t*>(p.pp_epoch);
             if (threadIdx.x == 64) {
@@ -316,22 +343,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             }
             publish();
         }
+        }   // FOLD
         if (p.do_fwd) {
             for (int l = 1; l <= L; ++l) {
                 const ChainLayer& ly = p.layers[l - 1];
                 const bool m_ok = m < ly.out;
                 const float bias = m_ok ? __ldg(p.W + ly.w_off + (int64_t)m * ly.ldw + ly.in) : 0.f;
                 const bool is_logits = (l == L) && p.do_loss;
-                const int rot_f = acc_split ? acc_rotation((ly.in + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;   // as the MMA warp chose
-                // loss head: the targets do not depend on the MMA - fetch this lane's row before waiting for the logits
-                // (the head is ONE warp on the critical path between the last forward and the first backward GEMM)
-                float tg_pre[16];
-                const bool head_pre = p.head_prefetch && is_logits && q == 0 && half == 0 && ly.out <= 16;
-                if (head_pre) {
-                    const float* __restrict__ tgp = p.target + (int64_t)(row0 + lane) * p.ldt;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) tg_pre[k] = (k < ly.out && lane < p.mb_rows) ? __ldg(tgp + k) : 0.f;
-                }
+                const int nkb_f = (ly.in + (int)kBlockK - 1) / (int)kBlockK;
+                const bool acc_f = acc_split && nkb_f >= 8;   // as the MMA warp chose: extra accumulators for long reductions only
                 mbar_wait(tmem_full_bar, tmem_waits & 1);
                 ++tmem_waits;
                 tc_fence_after();
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     float keep[16];
                     for (int c = c_lo; c < c_hi; c += 16) {
                         float v[16];
-                        tmem_ld16_acc(taddr + c, small_off, v, rot_f, (uint32_t)N);
+                        if (acc_f) tmem_ld16_acc(taddr + c, small_off, v, acc_rotation(nkb_f, N, kTmemBudget), (uint32_t)N); else tmem_ld16(taddr + c, v);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float x = v[j] + bias;
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             else if (m_ok && n < p.mb_rows) {
                                 gout[(int64_t)n * p.act_ld[l] + m] = x;
                                 if (SPLIT) p.act_lo[l][(int64_t)(row0 + n) * p.act_ld[l] + m] = tf32_lo(x);
-                                if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[l] + m] = x;
+                                if constexpr (FOLD) { if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[l] + m] = x; }
                             }
                         }
                     }
@@ -369,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                             if (c_lo + j < p.mb_rows) {
                                 gout[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
                                 if (SPLIT) p.act_lo[l][(int64_t)(row0 + c_lo + j) * p.act_ld[l] + m] = tf32_lo(keep[j]);
-                                if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j];
+                                if constexpr (FOLD) { if (l == L && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[l] + m] = keep[j]; }
                             }
                     }
                     wbuf ^= 1;
@@ -386,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                     if (q == 0 && half == 0) {
                         for (int c = 0; c < N; c += 16) {
                             float v[16];
-                            tmem_ld16_acc(taddr + c, small_off, v, rot_f, (uint32_t)N);
+                            if (acc_f) tmem_ld16_acc(taddr + c, small_off, v, acc_rotation(nkb_f, N, kTmemBudget), (uint32_t)N); else tmem_ld16(taddr + c, v);
                             if (m < C) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) scratch[(c + j) * kScratchLd + m] = v[j] + bias;
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                                 float ssum = 0.f;
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) {
-                                    tgv[k] = (head_pre && n == lane) ? tg_pre[k] : ((k < C && row_ok) ? __ldg(tg + k) : 0.f);
+                                    tgv[k] = (k < C && row_ok) ? __ldg(tg + k) : 0.f;
                                     ev[k] = (k < C) ? expf(zr[k] - gmax) : 0.f;
                                     ssum += ev[k];
                                 }
@@ -475,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                 }
             }
         }
-        if (p.do_fwd && !p.do_bwd && p.out_peer != nullptr) {
+        if (FOLD && p.do_fwd && !p.do_bwd && p.out_peer != nullptr) {
             // the stage's output tile is in the next stage's receive slot: one fence, then its arrival flag
             asm volatile("bar.sync 2, 256;" ::: "memory");
             if (threadIdx.x == 64) {
@@ -507,7 +527,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
             for (int l = L; l >= bwd_lo; --l) {
                 const ChainLayer& ly = p.layers[l - 1];
                 const bool m_ok = m < ly.in;                 // output feature of dgrad = input feature of layer l
-                const int rot_b = acc_split ? acc_rotation((ly.out + (int)kBlockK - 1) / (int)kBlockK, N, kTmemBudget) : 1;
                 const bool mask_on = (l >= 2) && p.layers[l - 2].relu;
                 const float* __restrict__ yprev = p.act[l - 1] + (int64_t)row0 * p.act_ld[l - 1];
                 float* __restrict__ gprev = p.dz[l - 1] + (int64_t)row0 * p.act_ld[l - 1];
@@ -537,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         else mk[j] = (mask_on && m_ok && n < p.mb_rows) ? yprev[(int64_t)n * p.act_ld[l - 1] + m] : 1.f;
                     }
                     float v[16];
-                    tmem_ld16_acc(taddr + c, small_off, v, rot_b, (uint32_t)N);
+                    tmem_ld16(taddr + c, v);   // backward reductions run over <= 128 output features: one accumulator
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int n = c + j;
@@ -548,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         else if (m_ok && n < p.mb_rows) {
                             gprev[(int64_t)n * p.act_ld[l - 1] + m] = x;
                             if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + n) * p.act_ld[l - 1] + m] = tf32_lo(x);
-                            if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[0] + m] = x;
+                            if constexpr (FOLD) { if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)n * p.act_ld[0] + m] = x; }
                         }
                     }
                 }
@@ -562,12 +581,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
                         if (c_lo + j < p.mb_rows) {
                             gprev[(int64_t)(c_lo + j) * p.act_ld[l - 1] + m] = keep[j];
                             if (SPLIT) p.dz_lo[l - 1][(int64_t)(row0 + c_lo + j) * p.act_ld[l - 1] + m] = tf32_lo(keep[j]);
-                            if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[0] + m] = keep[j];
+                            if constexpr (FOLD) { if (l == 1 && p.out_peer != nullptr) p.out_peer[(int64_t)(c_lo + j) * p.act_ld[0] + m] = keep[j]; }
                         }
                 }
                 signal_ready(l - 1);
             }
-            if (p.out_peer != nullptr && !p.first_stage) {
+            if (FOLD && p.out_peer != nullptr && !p.first_stage) {
                 // dz[0] is in the previous stage's receive slot: one fence, then its arrival flag
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (threadIdx.x == 64) {
@@ -672,14 +691,23 @@ void chain_plan_free(ChainPlan* plan) {
 }
 
 cudaError_t chain_configure() {
-    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mlp_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
-    if (plan.p.split) mlp_chain_kernel<true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
-    else mlp_chain_kernel<false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+    const ChainParams& p = plan.p;
+    const bool fold = p.in_flag != nullptr || p.out_peer != nullptr || p.x_from_global != 0;
+    if (p.split) {
+        if (fold) mlp_chain_kernel<true, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+        else mlp_chain_kernel<true, false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+    } else {
+        if (fold) mlp_chain_kernel<false, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+        else mlp_chain_kernel<false, false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -144,6 +144,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // (measured: error grows linearly with the number of accumulate steps, ~0.7 * n * 2^-24 relative), so keeping the small
 // terms out of the main chain cuts the steps that matter by 3x; the two are added here in fp32 (round to nearest).
 // small_off == 0: single accumulator (TF32 mode).
+// two accumulators, both loads in flight before ONE wait (the common 3xTF32 case: one main accumulator + the small one)
+__device__ __forceinline__ void tmem_ld16_pair(uint32_t taddr, uint32_t small_off, float (&v)[16]) {
+    uint32_t r[16], w[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+          "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+        : "r"(taddr + small_off)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(w[i]);
+}
 // Long reductions additionally rotate the hi*hi products of successive k-blocks over `n_main` main accumulators
 // (`main_stride` columns apart): each chain is n_main times shorter; the partial sums are added here.
 __device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, uint32_t small_off, float (&v)[16], int n_main = 1, uint32_t main_stride = 0u) {

@@ -152,6 +152,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
             const uint32_t idesc = umma_idesc_tf32(kBlockM, p.block_n, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
             const uint32_t a_hi = A_MN ? umma_desc_hi(512u, 1u) : umma_desc_hi(1024u, 2u);
             const uint32_t b_hi = B_MN ? umma_desc_hi(512u, 1u) : umma_desc_hi(1024u, 2u);
+            uint32_t rot_i = 0u;                          // main accumulator of the current k-block (round robin)
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (kb / p.stages) & 1;
@@ -168,15 +169,18 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                     if (p.split) {
                         // fp32-equivalent product: small terms first, then hi*hi (the raw tiles ARE the hi parts)
                         const uint32_t al_lo = a_lo + (half_bytes >> 4), bl_lo = b_lo + (half_bytes >> 4);
+                        // accumulators of this k-block as plain registers (no modulo in the issue loop: the uniform datapath is slow)
+                        const uint32_t small_acc = tmem_base + small_off;
+                        const uint32_t main_acc = tmem_base + rot_i * (uint32_t)p.block_n;
+                        const bool main_fresh = acc_split && kb < rot;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint32_t main_acc = tmem_base + (uint32_t)(kb % rot) * (uint32_t)p.block_n;
-                            umma_tf32(tmem_base + small_off, umma_desc_pack(al_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
-                                      idesc, (kb | k4) != 0 ? 1u : 0u);
-                            umma_tf32(tmem_base + small_off, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
+                            umma_tf32(small_acc, umma_desc_pack(al_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
+                                      idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
+                            umma_tf32(small_acc, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(bl_lo + k4 * b_step, b_hi),
                                       idesc, 1u);
                             umma_tf32(main_acc, umma_desc_pack(a_lo + k4 * a_step, a_hi), umma_desc_pack(b_lo + k4 * b_step, b_hi),
-                                      idesc, (!acc_split || kb >= rot || k4 != 0) ? 1u : 0u);
+                                      idesc, (main_fresh && k4 == 0) ? 0u : 1u);
                         }
                     } else
 #pragma unroll
@@ -186,6 +190,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& tmA, const CUten
                     umma_commit(empty_bar(s));                // smem stage free once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
                 }
+                rot_i = (rot_i + 1u == (uint32_t)rot) ? 0u : rot_i + 1u;   // every lane keeps the round-robin index (any lane may be elected)
                 __syncwarp();
             }
         }

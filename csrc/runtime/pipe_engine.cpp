@@ -263,7 +263,6 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.dbg = nullptr;
     cp.sync_debug = (getenv("SSB_RACECHECK") && atoi(getenv("SSB_RACECHECK")) > 0) ? 1 : 0;
     cp.acc_split = acc_split_default();
-    cp.head_prefetch = (getenv("SSB_HEAD_PREFETCH") && atoi(getenv("SSB_HEAD_PREFETCH")) == 0) ? 0 : 1;
     if (fold != nullptr && pp_ctx_ != nullptr) {
         cp.in_flag = fold->in_flag; cp.x_from_global = fold->x_from_global ? 1 : 0;
         cp.out_peer = fold->out_peer; cp.out_flag = fold->out_flag; cp.out_credit = fold->out_credit;

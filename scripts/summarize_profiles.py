@@ -90,7 +90,7 @@ def sass_census():
             if "fused_wgrad_dp" in name:
                 short = "fused_wgrad_dp"
             elif "mlp_chain_kernel" in name:
-                short = "mlp_chain_" + ("fp32" if "ILb1E" in name else "tf32")
+                short = "mlp_chain_" + ("fp32" if "ILb1E" in name else "tf32") + ("_fold" if "Lb1EEEv" in name else "")
             elif "dp_ll_wgrad" in name:
                 short = "dp_ll_dp" + re.search(r"ILi(\d)E", name).group(1)
             elif "tc_wgrad_group" in name:
