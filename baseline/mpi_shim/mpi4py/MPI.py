@@ -68,8 +68,18 @@ class _ShmGroup:
 
     @staticmethod
     def _spin(arr, idx, target):
+        """busy-wait on a shared counter; a dead peer must not hang the job forever (the bench has a wall-clock budget)"""
+        import time
+
+        n = 0
+        t0 = None
         while arr[idx] < target:
-            pass
+            n += 1
+            if (n & 0xFFFF) == 0:
+                if t0 is None:
+                    t0 = time.monotonic()
+                elif time.monotonic() - t0 > float(os.environ.get("SSB_REF_SHM_TIMEOUT_S", "300")):
+                    raise RuntimeError("mpi4py shim: peer did not reach the shared-memory rendezvous (dead rank?)")
 
     def allreduce_(self, arr):
         """in-place SUM over the group, rank order (every rank computes the identical result)"""
