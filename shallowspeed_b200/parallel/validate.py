@@ -454,9 +454,18 @@ def max_in_flight(schedule) -> int:
 # replays that lowering for all stages over several steps and reports a deadlock if the stream programs can block each
 # other (e.g. a flag wait queued in front of a push the neighbour is waiting for).
 # ------------------------------------------------------------------------------------------------------------
-def simulate_one_sided(schedules: Sequence, n_steps: int = 3, n_mu_streams: int = 4, sends_first: bool = True) -> dict:
+def simulate_one_sided(schedules: Sequence, n_steps: int = 3, n_mu_streams: int = 4, sends_first: bool = True,
+                       layout: str = "comm_stream") -> dict:
     """``sends_first=False`` models the WRONG lowering (flag waits queued in front of the pushes of the same group) and
-    exists so the tests can show that this model does detect the resulting cross-stage deadlock."""
+    exists so the tests can show that this model does detect the resulting cross-stage deadlock.
+
+    ``layout`` selects how the executor places the transport ops:
+      * ``"comm_stream"``  - every push / flag wait on the stage's one communication stream (big boundary tiles);
+      * ``"mubatch"``      - small tiles (the default lowering since round 2): the push sits on the stream of the micro-batch
+        that produced the tile, right behind its compute op, the flag wait on the stream of the micro-batch that consumes
+        it, right in front of its compute op.  The FOLDED lowering (wait and push inside the chain kernel launch) is the
+        same program with [wait, compute, push] fused into one launch, so this layout models it as well."""
+    assert layout in ("comm_stream", "mubatch")
     S = len(schedules)
     progs = []          # per stage: {stream name: [op, ...]}, op = (kind, payload)
     for s, sc in enumerate(schedules):
@@ -465,6 +474,17 @@ def simulate_one_sided(schedules: Sequence, n_steps: int = 3, n_mu_streams: int 
         ev_in, ev_gout, ev_fwd, ev_bwd = {}, {}, {}, {}
         n_ev = 0
         for it in _itemize(stream):
+            if it.kind == "group" and layout == "mubatch":
+                mu_of = _resolve_group_mubatches(stream, it)
+                for ins in it.instrs:
+                    mu = mu_of[id(ins)]
+                    ops = streams.setdefault(f"c{mu % n_mu_streams}", [])
+                    if isinstance(ins, (SendActivations, SendInputGrad)):
+                        is_act = isinstance(ins, SendActivations)
+                        ops.append(("push", ("act" if is_act else "dz", s + 1 if is_act else s - 1, mu)))
+                    else:
+                        ops.append(("wait_flag", ("act" if isinstance(ins, RecvActivations) else "dz", s, mu)))
+                continue
             if it.kind == "group":
                 recvs = []
                 sends = [i for i in it.instrs if isinstance(i, (SendActivations, SendInputGrad))]

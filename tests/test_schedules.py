@@ -215,6 +215,21 @@ def test_one_sided_transport_model_is_deadlock_free(cls):
                 assert stats["pushes"] == stats["waits"] == 3 * per_step
 
 
+@pytest.mark.parametrize("cls", [NaiveParallelSchedule, GPipeSchedule, PipeDreamSchedule, InferenceSchedule])
+def test_one_sided_transport_on_microbatch_streams_is_deadlock_free(cls):
+    """The lowering used since round 2 for small boundary tiles - and, fused into one launch, by the folded chain kernel:
+    a micro-batch's flag wait, compute and push all sit on that micro-batch's stream.  Micro-batches that share a stream
+    (fewer streams than micro-batches in flight) keep the instruction order of the schedule on it."""
+    from shallowspeed_b200.parallel.validate import simulate_one_sided
+
+    for M in (1, 2, 4, 5, 8):
+        for S in (2, 3, 4, 8):
+            for nms in (1, 2, 4, 8):
+                stats = simulate_one_sided([cls(M, S, s) for s in range(S)], n_steps=3, n_mu_streams=nms, layout="mubatch")
+                per_step = (S - 1) * M * (1 if cls is InferenceSchedule else 2)
+                assert stats["pushes"] == stats["waits"] == 3 * per_step
+
+
 def test_one_sided_model_detects_the_wrong_op_order():
     # flag waits queued in FRONT of the pushes of the same group: 1F1B's [SendAct, RecvGrad] / [SendGrad, RecvAct] pairs
     # then wait for each other across the stage boundary
