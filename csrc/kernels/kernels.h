@@ -243,7 +243,7 @@ struct ChainParams {
     float* out_peer;
     uint32_t* out_flag;
     const uint32_t* out_credit;
-    int acc_split;                   // 3xTF32: small cross terms in their own accumulator + rotating main accumulators (ptx.cuh); 0 = one accumulator
+    int acc_split;                   // 3xTF32: launch the instantiation with separate + rotating accumulators for long reductions (SSB_CHAIN_ACC=1)
     int sync_debug;                  // SSB_RACECHECK=1: an explicit named barrier among the epilogue warps per layer, so that
                                      // compute-sanitizer's racecheck (which cannot see tcgen05.commit -> mbarrier ordering) can
                                      // verify the reuse of the activation ping-pong tiles

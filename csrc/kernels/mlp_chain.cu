@@ -62,7 +62,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 // FOLD (pipeline boundaries inside the kernel, see ChainParams) is a compile-time switch as well: merely carrying that code
 // - a prologue, two predicated peer stores per element in the epilogues - cost the single-GPU / data-parallel step 8 us
 // (same-box bisect, profiles/variants_r2.md), so launches without a folded boundary use the instantiation without it.
-template <bool SPLIT, bool FOLD>
+// ACC (3xTF32 only): separate + rotating accumulators for long reductions (layer 1, K = 784: error 2.9x cuBLAS fp32 instead
+// of 22x, profiles/precision_r2.md).  Compile-time as well, and OFF by default for this kernel: the same one-call, same-box
+// comparison of build variants showed that carrying that code costs 6 us per step (85.0 vs 79.2 us) whether or not it runs.
+// `SSB_CHAIN_ACC=1` selects the accurate instantiation; the per-layer GEMM kernels (wide layers) always use the scheme.
+template <bool SPLIT, bool FOLD, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const ChainParam
         reinterpret_cast<volatile uint32_t*>(smem_gen + p.stages * stage_bytes + n_abuf * abuf_bytes + 8u * (2 * p.stages + 2));
     // 3xTF32: up to 4 rotating main accumulators (long reductions only: layer 1) + one for the small cross terms, see ptx.cuh
     constexpr int kTmemBudget = 512;
-    const bool acc_split = SPLIT && p.acc_split != 0;
+    constexpr bool acc_split = SPLIT && ACC;
     const int max_rot = acc_split ? acc_rotation(1 << 20, N, kTmemBudget) : 1;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)N * (acc_split ? (uint32_t)max_rot + 1u : 1u)) tmem_cols <<= 1;
@@ -690,24 +694,34 @@ void chain_plan_free(ChainPlan* plan) {
     plan->maps_dev = nullptr;
 }
 
+template <bool SPLIT, bool FOLD, bool ACC>
+static cudaError_t chain_configure_one() {
+    return cudaFuncSetAttribute(mlp_chain_kernel<SPLIT, FOLD, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 cudaError_t chain_configure() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mlp_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mlp_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if ((e = chain_configure_one<false, false, false>()) != cudaSuccess) return e;
+    if ((e = chain_configure_one<false, true, false>()) != cudaSuccess) return e;
+    if ((e = chain_configure_one<true, false, false>()) != cudaSuccess) return e;
+    if ((e = chain_configure_one<true, true, false>()) != cudaSuccess) return e;
+    if ((e = chain_configure_one<true, false, true>()) != cudaSuccess) return e;
+    return chain_configure_one<true, true, true>();
 }
 
 cudaError_t chain_launch(const ChainPlan& plan, cudaStream_t stream) {
     const ChainParams& p = plan.p;
     const bool fold = p.in_flag != nullptr || p.out_peer != nullptr || p.x_from_global != 0;
-    if (p.split) {
-        if (fold) mlp_chain_kernel<true, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
-        else mlp_chain_kernel<true, false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+    const bool acc = p.split && p.acc_split != 0;
+#define SSB_CHAIN_LAUNCH(S, F, A) mlp_chain_kernel<S, F, A><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p)
+    if (!p.split) {
+        if (fold) SSB_CHAIN_LAUNCH(false, true, false); else SSB_CHAIN_LAUNCH(false, false, false);
+    } else if (!acc) {
+        if (fold) SSB_CHAIN_LAUNCH(true, true, false); else SSB_CHAIN_LAUNCH(true, false, false);
     } else {
-        if (fold) mlp_chain_kernel<false, true><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
-        else mlp_chain_kernel<false, false><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(p);
+        if (fold) SSB_CHAIN_LAUNCH(true, true, true); else SSB_CHAIN_LAUNCH(true, false, true);
     }
+#undef SSB_CHAIN_LAUNCH
     return cudaGetLastError();
 }
 

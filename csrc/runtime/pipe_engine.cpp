@@ -262,7 +262,7 @@ int PipeEngine::add_chain(int stream, int mu_base, int n_mu, bool do_fwd, bool d
     cp.do_fwd = do_fwd; cp.do_loss = do_loss; cp.do_bwd = do_bwd; cp.first_stage = cfg_.is_first;
     cp.dbg = nullptr;
     cp.sync_debug = (getenv("SSB_RACECHECK") && atoi(getenv("SSB_RACECHECK")) > 0) ? 1 : 0;
-    cp.acc_split = acc_split_default();
+    cp.acc_split = (getenv("SSB_CHAIN_ACC") && atoi(getenv("SSB_CHAIN_ACC")) > 0) ? 1 : 0;   // accurate instantiation, see mlp_chain.cu
     if (fold != nullptr && pp_ctx_ != nullptr) {
         cp.in_flag = fold->in_flag; cp.x_from_global = fold->x_from_global ? 1 : 0;
         cp.out_peer = fold->out_peer; cp.out_flag = fold->out_flag; cp.out_credit = fold->out_credit;

@@ -90,7 +90,8 @@ def sass_census():
             if "fused_wgrad_dp" in name:
                 short = "fused_wgrad_dp"
             elif "mlp_chain_kernel" in name:
-                short = "mlp_chain_" + ("fp32" if "ILb1E" in name else "tf32") + ("_fold" if "Lb1EEEv" in name else "")
+                m3 = re.search(r"ILb(\d)ELb(\d)ELb(\d)E", name)
+                short = "mlp_chain_" + ("fp32" if m3.group(1) == "1" else "tf32") + ("_fold" if m3.group(2) == "1" else "") + ("_acc" if m3.group(3) == "1" else "")
             elif "dp_ll_wgrad" in name:
                 short = "dp_ll_dp" + re.search(r"ILi(\d)E", name).group(1)
             elif "tc_wgrad_group" in name:

@@ -151,3 +151,25 @@ def test_default_training_step_is_a_two_or_three_node_line(monkeypatch, precisio
     assert int(tr.engine.graph_nodes()) == want
     got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
     assert got == ref and torch.equal(tr.model.arena.weights, base.model.arena.weights)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Chain kernel, accurate instantiation (SSB_CHAIN_ACC=1): separate + rotating TMEM accumulators for the K = 784 reduction
+# of layer 1.  Not bit-identical to the default instantiation (different summation order) - it must train the same
+# model within fp32 rounding, and stay at least as close to the fp64 forward of layer 1.
+# ---------------------------------------------------------------------------------------------------------
+def test_chain_accurate_accumulator_instantiation_trains_the_same_model(monkeypatch):
+    from shallowspeed_b200.dataset import synthetic_mnist
+    from shallowspeed_b200.parallel.engine import Trainer
+
+    x, y = synthetic_mnist(n=128 * 4)
+    xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("SSB_CHAIN_ACC", "0")
+    base = Trainer(SIZES, lr=0.1, precision="fp32")
+    ref = [base.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    monkeypatch.setenv("SSB_CHAIN_ACC", "1")
+    tr = Trainer(SIZES, lr=0.1, precision="fp32")
+    got = [tr.step(xh[i * 128:(i + 1) * 128], yh[i * 128:(i + 1) * 128]) for i in range(4)]
+    assert all(abs(a - b) <= 2e-5 * max(1.0, abs(b)) for a, b in zip(got, ref)), (got, ref)
+    wa, wb = tr.model.arena.weights, base.model.arena.weights
+    assert float((wa - wb).norm() / wb.norm()) < 1e-5
