@@ -300,8 +300,9 @@ def run_ours(args):
             "impl": "ours", "metric": "MLP training samples/sec (whole job)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": ("fp32 (storage + accumulate fp32; products on tcgen05 as 3xTF32 = lo*hi + hi*lo + hi*hi in separate / rotating "
-                      "TMEM accumulators; measured error 8.5e-7 at K=784 vs 2.9e-7 for cuBLAS fp32, profiles/precision_r2.md)"
+            "dtype": ("fp32 (storage + accumulate fp32; products on tcgen05 as 3xTF32 = lo*hi + hi*lo + hi*hi; measured error vs an fp64 "
+                      "oracle at K=784: 6.4e-6 with the default chain-kernel instantiation, 8.5e-7 with SSB_CHAIN_ACC=1, "
+                      "cuBLAS fp32 2.9e-7 - profiles/precision_r2.md)"
                       if args.precision == "fp32" else "tf32 (fp32 storage + accumulate, single-pass tf32 products)"),
             "data": "synthetic MNIST-shaped, random-init weights",
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
