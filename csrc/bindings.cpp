@@ -227,6 +227,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         const int per = splits > 0 ? (num_kb + splits - 1) / splits : num_kb;
         return std::make_tuple(splits, per, (int)plan.grid.z, plan.p.stages, plan.smem_bytes, err);
     });
+    // LL data-parallel kernel: host-side geometry (tiles per layer, lines per landing zone), callable without a GPU
+    m.def("dp_ll_tiles", [](int in, int out) { return ssb::dp_ll_tiles(in, out); });
+    m.def("dp_ll_zone_lines", [](int dp, int n_tiles) { return (int64_t)ssb::dp_ll_zone_lines(dp, n_tiles); });
     // Exercises the C++ runtime features that break when libstdc++ is linked statically next to torch's dynamic
     // copy (the round-1 GPU-suite segfault): locale-dependent integer / float formatting and an exception that
     // crosses a function boundary.  Callable without a GPU (tests/test_native_linkage.py).

@@ -7,6 +7,10 @@ flight), gradient *accumulation* into ``param.grad``, and the grad-hook /
 post-grad-hook protocol ``Sequential.backward`` drives so that the DP all-reduce of
 layer *l* can overlap the backward of layer *l-1* (layers.py:201-213).
 
+The class skeleton is the reference's on purpose: ``Module`` / ``ReLU`` / ``Softmax`` / ``Sequential`` keep its method names,
+cache keys (``bitmask_{id}`` / ``input_{id}``) and hook loops, because that API surface IS the parity requirement
+(layers.py:31-96, 169-233).  What is new here is everything underneath it:
+
 B200-first differences (design, not translation):
 
 * storage is ``torch.Tensor``; all parameters of a pipeline stage live in ONE flat

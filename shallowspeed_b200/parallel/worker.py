@@ -20,6 +20,10 @@ Differences to the reference VM, all deliberate:
 * the reference's stage>0 GPipe path receives in place into the array its first Linear
   cached by reference (pipe.py:371-373 + layers.py:116-117), silently corrupting the
   stashed input of earlier micro-batches; here every in-flight micro-batch owns a slot.
+
+The instruction -> handler table and the handler names mirror the reference's ``Worker`` (pipe.py:389-432) by design:
+it is the portable, debuggable VM with the reference's surface.  Slots, grouped communication, per-layer bucketing and
+everything performance-relevant live in the native executor (``parallel/engine.py`` + ``csrc/runtime``).
 """
 from __future__ import annotations
 
