@@ -225,7 +225,7 @@ def run_ours(args):
 
     for i in range(max(3, args.warmup)):
         dev_step(counter[0]); counter[0] += 1
-    with ClockSampler(local_rank, period_ms=20) as clk:
+    with ClockSampler(local_rank, period_ms=5) as clk:
         dev_samples = timed_blocks(dev_step, args.steps, args.repeats, stream)
         for i in range(max(3, args.warmup // 4)):
             e2e_step(counter[0]); counter[0] += 1

@@ -60,14 +60,51 @@ _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons in a background process while a
-    timed region runs (B200_PROFILING.md "clocks DURING the timed region")."""
+    """Samples SM clocks / power / throttle reasons while a timed region runs (B200_PROFILING.md "clocks DURING the timed
+    region").  Preferred source: NVML in-process (a thread polling every ``period_ms``; works for regions of a few
+    milliseconds - the driver times 20 steps of ~0.1 ms); fallback: an ``nvidia-smi -lms`` child process, which needs
+    ~100 ms to deliver its first line."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int = 0, period_ms: int = 100):
         self.gpu_index, self.period_ms = gpu_index, period_ms
         self.proc, self.lines, self._thr = None, [], None
+        self._nvml, self._stop, self._samples = None, threading.Event(), []
+
+    # ---- NVML path
+    def _nvml_start(self) -> bool:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h, mx)
+        except Exception:
+            self._nvml = None
+            return False
+
+        def pump():
+            pynvml, h, mx = self._nvml
+            period = max(self.period_ms, 2) / 1e3
+            while not self._stop.is_set():
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
+                    rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    self._samples.append((sm, mx, pw, rs))
+                except Exception:
+                    pass
+                self._stop.wait(period)
+
+        self._thr = threading.Thread(target=pump, daemon=True)
+        self._thr.start()
+        return True
 
     def __enter__(self):
+        if self._nvml_start():
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={_QUERY}", "--format=csv,noheader,nounits",
@@ -84,6 +121,9 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc):
+        self._stop.set()
+        if self._nvml is not None and self._thr is not None:
+            self._thr.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -94,6 +134,12 @@ class ClockSampler:
 
     def summary(self) -> dict:
         sm, mx, reasons, power = [], [], set(), []
+        if self._nvml is not None:
+            for c, m, p, r in self._samples:
+                sm.append(c); mx.append(m); power.append(p)
+                for name, bit in self._REASONS:
+                    if r & bit:
+                        reasons.add(name)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -110,7 +156,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         busy = [c for c, p in zip(sm, power) if p > 0.3 * max(power)] or sm
         return {"sm_mhz": median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+                "samples": len(sm), "power_w_max": max(power), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 class StepLogger:
