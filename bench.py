@@ -186,6 +186,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     counter = [0]
+    sampler = [None]
 
     def timed_blocks(step_fn, n, repeats, on_stream):
         """`repeats` blocks of exactly `n` steps, each bracketed by barrier + synchronize on both sides and timed with
@@ -202,6 +203,8 @@ def run_ours(args):
             for _i in range(n):
                 step_fn(counter[0]); counter[0] += 1
             e1.record(on_stream)
+            if sampler[0] is not None:
+                sampler[0].sample_now()                # the device is still working through the block: clocks under load
             barrier()
             out.append(e0.elapsed_time(e1))
         return out
@@ -226,11 +229,13 @@ def run_ours(args):
     for i in range(max(3, args.warmup)):
         dev_step(counter[0]); counter[0] += 1
     with ClockSampler(local_rank, period_ms=5) as clk:
+        sampler[0] = clk
         dev_samples = timed_blocks(dev_step, args.steps, args.repeats, stream)
         for i in range(max(3, args.warmup // 4)):
             e2e_step(counter[0]); counter[0] += 1
         e2e_samples = timed_blocks(e2e_step, args.steps, args.repeats, stream)
         losses.append(trainer.flush())
+    sampler[0] = None
     ms_dev, dev_blocks = reduce_blocks(dev_samples)
     ms_e2e, e2e_blocks = reduce_blocks(e2e_samples)
     clocks = clk.summary()

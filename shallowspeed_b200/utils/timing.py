@@ -102,6 +102,18 @@ class ClockSampler:
         self._thr.start()
         return True
 
+    def sample_now(self):
+        """one synchronous NVML sample from the calling thread (the bench calls this while a timed block is still in flight on
+        the device: the polling thread competes with the step loop for the GIL and may get few turns in a 2 ms region)"""
+        if self._nvml is None:
+            return
+        try:
+            pynvml, h, mx = self._nvml
+            self._samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx,
+                                  pynvml.nvmlDeviceGetPowerUsage(h) / 1e3, int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+        except Exception:
+            pass
+
     def __enter__(self):
         if self._nvml_start():
             return self
