@@ -394,8 +394,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- grouped weight-gradient launch: the tiles of SEVERAL layers' WGRAD GEMMs in one grid (one table entry per CTA).
-// Removes the fork / join of one graph node per layer from the end of a step; with the zero-copy loss and the chain
-// kernel deriving its lo twins on chip the whole fp32 training step is two graph nodes: chain kernel -> grouped wgrad.
+// Removes the fork / join of one graph node per layer from the end of a step: with the zero-copy loss the fp32 training
+// step of a narrow stage is chain kernel -> grouped wgrad (+SGD) -> W_lo refresh (or chain || LL kernel under DP).
 __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_group_kernel(const GemmGroupEntry* __restrict__ entries) {
     const GemmGroupEntry& e = entries[blockIdx.x];
     const GemmParams p = e.p;                      // private copy: the body reads these fields in every loop

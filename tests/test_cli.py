@@ -70,6 +70,22 @@ def test_bench_reference_arm_json_contract():
     assert d["config"]["global_batch"] == 128 and d["config"]["n_mubatches"] == 4
 
 
+def test_blocking_ddp_contrast_script(tmp_path):
+    """scripts/ddp_blocking_mnist.py (reference: scripts/DDP_PyTorch_MNIST.py): 1 process, then 2 gloo ranks with a
+    blocking all-reduce per parameter; hashes agree across ranks and the divergence from the 1-process model is reported."""
+    script = os.path.join(ROOT, "scripts", "ddp_blocking_mnist.py")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    common = ["--epochs", "1", "--samples", "1280", "--device", "cpu"]
+    r = subprocess.run([sys.executable, script] + common, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (tmp_path / "data" / "models" / "model_p1.pkl").exists()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29671", script] + common, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("L1 divergence")]
+    assert line and float(line[0].rsplit(" ", 1)[1]) < 1.0      # same global batches, summation order differs
+
+
 def test_parsers_know_the_runtime_knobs():
     sys.path.insert(0, ROOT)
     try:
