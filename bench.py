@@ -125,7 +125,9 @@ def run_reference(args):
             "gpu_launches": 0,
             "config": {"model": "MLP 784-128-127-126-125-124-123-10", "global_batch": gbs, "n_mubatches": args.n_mubatches,
                        "parallelism": f"dp{dp}" + (f"xpp{args.pp}" if args.pp > 1 else ""), "schedule": sched,
-                       "device": "host CPUs (NumPy + mpi4py shim over gloo)",
+                       "device": "host CPUs (NumPy + mpi4py shim: " + ("single process" if args.gpus == 1 else
+                                  "shared-memory data path, gloo bootstrap" if os.environ.get("SSB_REF_SHM", "1") not in ("0", "")
+                                  else "gloo over TCP loopback") + ")",
                        "threads_per_rank": res["threads_per_rank"], "thread_sweep_ms_per_step": res.get("thread_sweep"),
                        "weights_dtype": res["weights_dtype"],
                        "timing": "wall clock between barriers, max over ranks (CPU code)"},
