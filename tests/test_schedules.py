@@ -238,3 +238,34 @@ def test_one_sided_model_detects_the_wrong_op_order():
     with pytest.raises(ScheduleError, match="deadlock in the one-sided transport model"):
         simulate_one_sided([PipeDreamSchedule(4, 2, s) for s in range(2)], sends_first=False)
     simulate_one_sided([PipeDreamSchedule(4, 2, s) for s in range(2)], sends_first=True)
+
+
+def test_random_pipeline_shapes_property():
+    """Property sweep over random (schedule, micro-batches, stages, stream count): rendezvous-valid, every micro-batch is
+    computed exactly once per stage and direction, the gradient all-reduce rides on the stage's final backward, the
+    activation stash never exceeds the schedule's slot count, and the one-sided transport replay terminates."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from shallowspeed_b200.parallel.validate import simulate_one_sided
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True)
+    @hyp.given(cls=st.sampled_from(TRAIN_SCHEDULES), M=st.integers(1, 24), S=st.integers(1, 10), nms=st.sampled_from([1, 2, 4, 8]),
+               layout=st.sampled_from(["comm_stream", "mubatch"]))
+    def check(cls, M, S, nms, layout):
+        validate(cls, M, S)
+        scheds = [cls(M, S, s) for s in range(S)]
+        for sc in scheds:
+            fl = flatten(list(sc.steps()))
+            fwd = [i.mubatch_id for i in fl if isinstance(i, pipe.Forward)]
+            bwd = [i.mubatch_id for i in fl if isinstance(i, (pipe.BackwardGradAcc, pipe.BackwardGradAllReduce))]
+            assert sorted(fwd) == sorted(bwd) == list(range(M))
+            assert isinstance(fl[0], pipe.ZeroGrad) and isinstance(fl[-1], pipe.OptimizerStep)
+            last_bwd = [i for i in fl if isinstance(i, (pipe.BackwardGradAcc, pipe.BackwardGradAllReduce))][-1]
+            assert isinstance(last_bwd, pipe.BackwardGradAllReduce)
+            assert sum(isinstance(i, pipe.BackwardGradAllReduce) for i in fl) == 1
+            assert max_in_flight(sc) <= max(1, getattr(sc, "num_slots", M)) <= M
+        if S > 1:
+            stats = simulate_one_sided(scheds, n_steps=2, n_mu_streams=nms, layout=layout)
+            assert stats["pushes"] == stats["waits"] == 2 * (S - 1) * M * 2
+
+    check()
