@@ -21,7 +21,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -140,7 +139,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from shallowspeed_b200.dataset import synthetic_mnist
-    from shallowspeed_b200.parallel.comm import ProcessGrid, SelfComm, make_torch_comms
+    from shallowspeed_b200.parallel.comm import ProcessGrid, make_torch_comms
     from shallowspeed_b200.parallel.engine import Trainer
     from shallowspeed_b200.utils.timing import ClockSampler, max_over_ranks
 

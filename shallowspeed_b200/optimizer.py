@@ -8,8 +8,6 @@ inside the wgrad+all-reduce kernel and ``step`` is not called at all.
 """
 from __future__ import annotations
 
-import torch
-
 
 class SGD:
     def __init__(self, parameters, lr: float, arena=None):

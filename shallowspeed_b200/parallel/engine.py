@@ -15,7 +15,7 @@ import torch
 
 from .comm import Comm, ProcessGrid, SelfComm, TorchComm
 from .instructions import encode, flatten
-from .schedules import InferenceSchedule, Schedule
+from .schedules import Schedule
 from .validate import simulate
 
 DP_MODE = {"none": 0, "nccl": 1, "fused": 2, "nvls": 3}
